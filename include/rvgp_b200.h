@@ -1,0 +1,98 @@
+/* rvgp_b200.h -- C ABI of librvgp_b200.so: hand-written sm_100a kernels for RVGP's
+ * geometry-and-spectral hot path.
+ *
+ * This is the drop-in boundary.  Every entry point takes plain pointers and sizes (no torch / numpy
+ * types).  Unless stated otherwise every pointer is a DEVICE pointer, matrices are row-major FP64,
+ * indices are int32, calls are asynchronous on the handle's stream, and no ownership is transferred:
+ * the caller allocates inputs, outputs and workspaces (sizes given by the *_workspace_bytes queries).
+ *
+ * The reference's only FFI is the CPython extension `ptu_dijkstra`
+ * (RVGP/lib/ptu_dijkstra.pyx: tangent_frames :33, connections :128, internal C signatures
+ * _geodesic_neigborhood_tangents :300-311 and _parallel_transport_dijkstra :221-229); the rest of its
+ * path calls NumPy/SciPy/sklearn/GPflow.  Each function below names the reference code it replaces.
+ *
+ * Return value: 0 (RVGP_OK) or a negative status; rvgp_last_error(h) gives the message.
+ */
+#ifndef RVGP_B200_H
+#define RVGP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* rvgp_handle_t;
+
+#define RVGP_OK 0
+#define RVGP_ERR_BAD_ARG (-1)        /* <-> ValueError, ptu_dijkstra.pyx:68-82,156-160 */
+#define RVGP_ERR_RANK_DEFICIENT (-2) /* <-> return code -1 / RuntimeError, pyx:119-123,427-428 */
+#define RVGP_ERR_CUDA (-3)
+#define RVGP_ERR_NCCL (-4)
+#define RVGP_ERR_NOT_SPD (-5)        /* Cholesky breakdown (tf.linalg.cholesky raises InvalidArgumentError) */
+#define RVGP_ERR_CAPACITY (-6)       /* caller-provided workspace too small */
+
+/* ---- handle ------------------------------------------------------------------------------------ */
+int rvgp_create(int device, rvgp_handle_t* out);
+int rvgp_destroy(rvgp_handle_t h);
+int rvgp_set_stream(rvgp_handle_t h, void* cuda_stream);
+const char* rvgp_last_error(rvgp_handle_t h);
+int rvgp_sm_count(rvgp_handle_t h);
+/* kernels launched through this handle since creation (bench.py "gpu_launches") */
+unsigned long long rvgp_launch_count(rvgp_handle_t h);
+int rvgp_version(void);
+
+/* ---- K9: block-CSR SpMM (replaces the ARPACK mat-vec inside geometry.py:73) ------------------------
+ * Y = alpha * (A @ X) + beta * X + gamma * W      (the Chebyshev three-term step when beta,gamma != 0)
+ * A: BSR, nbrows block rows, d x d FP64 blocks (row-major inside a block) in `vals` (may be NULL for
+ * the scalar graph Laplacian pattern mode: d == 1, value = deg_i on the diagonal entry and -1 elsewhere,
+ * geometry.py:61).  X, W, Y: (nbrows*d) x ncols row-major with leading dimensions ldx/ldw/ldy.
+ * W may be NULL when gamma == 0.  ncols in [1, 64].  Y must not alias X or W. */
+int rvgp_bsr_spmm_f64(rvgp_handle_t h, int nbrows, int d, const int32_t* indptr, const int32_t* indices,
+                      const double* vals, const double* X, int64_t ldx, const double* W, int64_t ldw,
+                      double* Y, int64_t ldy, int ncols, double alpha, double beta, double gamma);
+
+/* Chebyshev filter of degree `degree` applied in place to the ncols columns of V (scaled three-term
+ * recurrence, Zhou & Saad): damps [lo_cut, hi] and amplifies below lo_cut, normalised at `lo_spec`.
+ * work0, work1: two (nrows x ncols) scratch block vectors with leading dimension ldw.
+ * The whole degree loop runs inside this one call (degree SpMM launches on the handle's stream);
+ * on return the filtered block is in V. */
+int rvgp_cheb_filter_f64(rvgp_handle_t h, int nbrows, int d, const int32_t* indptr, const int32_t* indices,
+                         const double* vals, double* V, int64_t ldv, double* work0, double* work1,
+                         int64_t ldw, int ncols, int degree, double lo_spec, double lo_cut, double hi);
+
+/* ---- K10: dense FP64 kernels for orthogonalisation / Rayleigh-Ritz ---------------------------------
+ * C (m x n, ldc) = alpha * op(A) * op(B).  Layout flags say which index of each operand is contiguous:
+ *   a_kmajor = 0: A(i,k) = A[k*lda + i]  ("A is stored as K x M", e.g. V^T of a tall block vector)
+ *   a_kmajor = 1: A(i,k) = A[i*lda + k]
+ *   b_kmajor = 0: B(k,j) = B[k*ldb + j]
+ *   b_kmajor = 1: B(k,j) = B[j*ldb + k]
+ * scale_k (nullable, length K) multiplies A(i,k) by scale_k[k] (the spectral density S in
+ * kernels.py:61).  When split_k > 1 the K range is split over split_k CTAs per tile, partial tiles go
+ * to `workspace` (split_k*m*n doubles) and are reduced in a fixed order (deterministic). */
+int rvgp_dgemm_f64(rvgp_handle_t h, int m, int n, int64_t k, double alpha, const double* A, int64_t lda,
+                   int a_kmajor, const double* B, int64_t ldb, int b_kmajor, const double* scale_k,
+                   double* C, int64_t ldc, int split_k, double* workspace);
+int64_t rvgp_dgemm_workspace_bytes(int m, int n, int split_k);
+
+/* column-wise reductions over tall block vectors (deterministic two-stage) ---------------------------
+ * out[c] = sum_r A[r*lda+c] * B[r*ldb+c]           (ncols <= 1024).  workspace: rvgp_coldot_workspace_bytes */
+int rvgp_coldot_f64(rvgp_handle_t h, int64_t nrows, int ncols, const double* A, int64_t lda,
+                    const double* B, int64_t ldb, double* out, double* workspace);
+/* out[c] = sum_r (W[r,c] - theta[c] * V[r,c])^2    (squared residual norms of Ritz pairs) */
+int rvgp_resid_sq_f64(rvgp_handle_t h, int64_t nrows, int ncols, const double* W, int64_t ldw,
+                      const double* V, int64_t ldv, const double* theta, double* out, double* workspace);
+int64_t rvgp_coldot_workspace_bytes(int64_t nrows, int ncols);
+/* A[r,c] *= s[c] */
+int rvgp_colscale_f64(rvgp_handle_t h, int64_t nrows, int ncols, double* A, int64_t lda, const double* s);
+/* deterministic counter-based uniform(-1,1) fill: element (r,c) depends only on (seed, r, c0+c) */
+int rvgp_fill_uniform_f64(rvgp_handle_t h, int64_t nrows, int ncols, double* A, int64_t lda,
+                          uint64_t seed, int64_t col_offset);
+/* out[r, c] = in[perm[r], c] for r < nrows (row gather; used for the locality permutation) */
+int rvgp_gather_rows_f64(rvgp_handle_t h, int64_t nrows, int ncols, const double* in, int64_t ldin,
+                         const int32_t* perm, int block, double* out, int64_t ldout);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RVGP_B200_H */

@@ -1,0 +1,55 @@
+// Shared helpers for the rvgp_b200 CUDA kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/rvgp_b200.h"
+
+namespace rvgp {
+
+struct Handle {
+    int device;
+    cudaStream_t stream;
+    int sm_count;
+    char last_error[512];
+    unsigned long long launches;  // kernels launched through this handle (bench.py: gpu_launches)
+};
+
+inline Handle* H(rvgp_handle_t h) { return reinterpret_cast<Handle*>(h); }
+
+inline int set_error(Handle* h, int code, const char* fmt, const char* a = "", const char* b = "") {
+    if (h) snprintf(h->last_error, sizeof(h->last_error), fmt, a, b);
+    return code;
+}
+
+#define RVGP_CUDA_OK(h, expr)                                                               \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess)                                                              \
+            return rvgp::set_error((h), RVGP_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+#define RVGP_LAUNCH_OK(h, name)                                                             \
+    do {                                                                                    \
+        (h)->launches++;                                                                    \
+        cudaError_t _e = cudaGetLastError();                                                \
+        if (_e != cudaSuccess)                                                              \
+            return rvgp::set_error((h), RVGP_ERR_CUDA, "launch %s: %s", name, cudaGetErrorString(_e)); \
+    } while (0)
+
+#define RVGP_REQUIRE(h, cond, msg)                                                          \
+    do {                                                                                    \
+        if (!(cond)) return rvgp::set_error((h), RVGP_ERR_BAD_ARG, "%s (%s)", msg, #cond);  \
+    } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace rvgp

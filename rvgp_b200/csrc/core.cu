@@ -1,0 +1,38 @@
+// Handle management for librvgp_b200.so (see include/rvgp_b200.h).
+#include "common.cuh"
+
+using namespace rvgp;
+
+extern "C" int rvgp_version(void) { return 100; }
+
+extern "C" int rvgp_create(int device, rvgp_handle_t* out) {
+    if (!out) return RVGP_ERR_BAD_ARG;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return RVGP_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return RVGP_ERR_CUDA;
+    Handle* h = new Handle();
+    h->device = device;
+    h->stream = nullptr;
+    h->launches = 0;
+    h->last_error[0] = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete h; return RVGP_ERR_CUDA; }
+    h->sm_count = prop.multiProcessorCount;
+    *out = h;
+    return RVGP_OK;
+}
+
+extern "C" int rvgp_destroy(rvgp_handle_t hh) {
+    delete H(hh);
+    return RVGP_OK;
+}
+
+extern "C" int rvgp_set_stream(rvgp_handle_t hh, void* s) {
+    if (!hh) return RVGP_ERR_BAD_ARG;
+    H(hh)->stream = reinterpret_cast<cudaStream_t>(s);
+    return RVGP_OK;
+}
+
+extern "C" const char* rvgp_last_error(rvgp_handle_t hh) { return hh ? H(hh)->last_error : "null handle"; }
+extern "C" int rvgp_sm_count(rvgp_handle_t hh) { return hh ? H(hh)->sm_count : 0; }
+extern "C" unsigned long long rvgp_launch_count(rvgp_handle_t hh) { return hh ? H(hh)->launches : 0ull; }

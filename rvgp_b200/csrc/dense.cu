@@ -1,0 +1,299 @@
+// K10 / K13: FP64 dense kernels.
+//
+//  * rvgp_dgemm_f64: register-tiled DGEMM (128x128x16 CTA tile, 8x8 per thread, DFMA pipe) with
+//    selectable operand layouts, optional K-scaling (spectral density S, reference kernels.py:61) and a
+//    deterministic split-K for tall-skinny Gram products V^T W (orthogonalisation / Rayleigh-Ritz of the
+//    block eigensolver that replaces ARPACK's reorthogonalisation, reference geometry.py:73).
+//    tcgen05 has no FP64 kind, so this is the FP64-FMA-pipe roofline (DESIGN.md "K10/K13").
+//  * column-wise reductions and small utilities over tall block vectors (HBM-bound, read once).
+#include "common.cuh"
+
+namespace rvgp {
+
+constexpr int BM = 128, BN = 128, BK = 16, PADM = 2;
+
+template <bool A_KMAJOR, bool B_KMAJOR>
+__global__ void __launch_bounds__(256)
+dgemm_kernel(int M, int N, int64_t K, double alpha, const double* __restrict__ A, int64_t lda,
+             const double* __restrict__ B, int64_t ldb, const double* __restrict__ scale_k,
+             double* __restrict__ C, int64_t ldc, int split_k, double* __restrict__ ws) {
+    __shared__ __align__(16) double As[BK][BM + PADM];
+    __shared__ __align__(16) double Bs[BK][BN + PADM];
+    const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    // K range of this split (multiple of BK)
+    const int64_t ktiles = (K + BK - 1) / BK;
+    const int64_t tiles_per = (ktiles + split_k - 1) / split_k;
+    const int64_t kt0 = (int64_t)blockIdx.z * tiles_per;
+    const int64_t kt1 = (kt0 + tiles_per < ktiles) ? kt0 + tiles_per : ktiles;
+
+    double acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+
+    double ra[8], rb[8];
+    auto load_tiles = [&](int64_t kt) {
+        const int64_t k0 = kt * BK;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            int i, k;
+            if (A_KMAJOR) { k = t & 15; i = (t >> 4) + 16 * r; }
+            else          { i = t & 127; k = (t >> 7) + 2 * r; }
+            const int64_t gk = k0 + k;
+            const int gi = m0 + i;
+            double v = 0.0;
+            if (gi < M && gk < K) {
+                v = A_KMAJOR ? __ldg(A + (int64_t)gi * lda + gk) : __ldg(A + gk * lda + gi);
+                if (scale_k) v *= __ldg(scale_k + gk);
+            }
+            ra[r] = v;
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            int j, k;
+            if (B_KMAJOR) { k = t & 15; j = (t >> 4) + 16 * r; }
+            else          { j = t & 127; k = (t >> 7) + 2 * r; }
+            const int64_t gk = k0 + k;
+            const int gj = n0 + j;
+            double v = 0.0;
+            if (gj < N && gk < K) v = B_KMAJOR ? __ldg(B + (int64_t)gj * ldb + gk) : __ldg(B + gk * ldb + gj);
+            rb[r] = v;
+        }
+    };
+    auto store_tiles = [&]() {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            int i, k;
+            if (A_KMAJOR) { k = t & 15; i = (t >> 4) + 16 * r; }
+            else          { i = t & 127; k = (t >> 7) + 2 * r; }
+            As[k][i] = ra[r];
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            int j, k;
+            if (B_KMAJOR) { k = t & 15; j = (t >> 4) + 16 * r; }
+            else          { j = t & 127; k = (t >> 7) + 2 * r; }
+            Bs[k][j] = rb[r];
+        }
+    };
+
+    if (kt0 < kt1) load_tiles(kt0);
+    for (int64_t kt = kt0; kt < kt1; ++kt) {
+        store_tiles();
+        __syncthreads();
+        if (kt + 1 < kt1) load_tiles(kt + 1);   // global loads in flight while the tile is consumed
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            double a[8], b[8];
+#pragma unroll
+            for (int ii = 0; ii < 4; ++ii) {
+                const double2 v = *reinterpret_cast<const double2*>(&As[kk][2 * ty + 32 * ii]);
+                a[2 * ii] = v.x; a[2 * ii + 1] = v.y;
+            }
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const double2 v = *reinterpret_cast<const double2*>(&Bs[kk][2 * tx + 32 * jj]);
+                b[2 * jj] = v.x; b[2 * jj + 1] = v.y;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+
+    double* out = C;
+    int64_t ldo = ldc;
+    double sc = alpha;
+    if (split_k > 1) { out = ws + (int64_t)blockIdx.z * M * N; ldo = N; sc = 1.0; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int gi = m0 + 2 * ty + 32 * (i >> 1) + (i & 1);
+        if (gi >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int gj = n0 + 2 * tx + 32 * (j >> 1) + (j & 1);
+            if (gj < N) out[(int64_t)gi * ldo + gj] = sc * acc[i][j];
+        }
+    }
+}
+
+__global__ void splitk_reduce_kernel(int M, int N, int split_k, double alpha, const double* __restrict__ ws,
+                                     double* __restrict__ C, int64_t ldc) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)M * N) return;
+    double s = 0.0;
+    for (int z = 0; z < split_k; ++z) s += ws[(int64_t)z * M * N + idx];   // fixed order: deterministic
+    C[(idx / N) * ldc + (idx % N)] = alpha * s;
+}
+
+// ---- column reductions ------------------------------------------------------------------------------
+// stage 1: each CTA reduces a contiguous slab of rows for all columns; stage 2: fixed-order sum of slabs.
+constexpr int RED_ROWS_PER_CTA = 2048;
+
+template <int MODE>  // 0: sum A*B   1: sum (W - theta*V)^2  (A=W, B=V)
+__global__ void __launch_bounds__(256)
+colreduce_stage1(int64_t nrows, int ncols, const double* __restrict__ A, int64_t lda,
+                 const double* __restrict__ B, int64_t ldb, const double* __restrict__ theta,
+                 double* __restrict__ partial) {
+    // thread layout: 32 columns x 8 row-lanes per pass over a 32-column panel
+    __shared__ double sm[8][33];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int64_t r0 = (int64_t)blockIdx.x * RED_ROWS_PER_CTA;
+    const int64_t r1 = (r0 + RED_ROWS_PER_CTA < nrows) ? r0 + RED_ROWS_PER_CTA : nrows;
+    for (int c0 = 0; c0 < ncols; c0 += 32) {
+        const int c = c0 + cx;
+        double s = 0.0;
+        if (c < ncols) {
+            const double th = (MODE == 1) ? __ldg(theta + c) : 0.0;
+            for (int64_t r = r0 + ry; r < r1; r += 8) {
+                const double a = __ldg(A + r * lda + c), b = __ldg(B + r * ldb + c);
+                if (MODE == 0) s = fma(a, b, s);
+                else { const double d = a - th * b; s = fma(d, d, s); }
+            }
+        }
+        sm[ry][cx] = s;
+        __syncthreads();
+        if (ry == 0 && c < ncols) {
+            double tot = 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) tot += sm[k][cx];
+            partial[(int64_t)blockIdx.x * ncols + c] = tot;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void colreduce_stage2(int nslabs, int ncols, const double* __restrict__ partial, double* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncols) return;
+    double s = 0.0;
+    for (int k = 0; k < nslabs; ++k) s += partial[(int64_t)k * ncols + c];
+    out[c] = s;
+}
+
+__global__ void colscale_kernel(int64_t nrows, int ncols, double* __restrict__ A, int64_t lda, const double* __restrict__ s) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nrows * ncols) return;
+    const int64_t r = idx / ncols;
+    const int c = (int)(idx % ncols);
+    A[r * lda + c] *= __ldg(s + c);
+}
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+__global__ void fill_uniform_kernel(int64_t nrows, int ncols, double* __restrict__ A, int64_t lda, uint64_t seed,
+                                    int64_t col_offset) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nrows * ncols) return;
+    const int64_t r = idx / ncols;
+    const int64_t c = idx % ncols + col_offset;
+    const uint64_t hsh = splitmix64(splitmix64(seed ^ (uint64_t)r * 0x100000001B3ull) + (uint64_t)c);
+    A[r * lda + (c - col_offset)] = (double)(hsh >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+}
+
+__global__ void gather_rows_kernel(int64_t nrows, int ncols, const double* __restrict__ in, int64_t ldin,
+                                   const int* __restrict__ perm, int block, double* __restrict__ out, int64_t ldout) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nrows * ncols) return;
+    const int64_t r = idx / ncols;
+    const int c = (int)(idx % ncols);
+    const int64_t src = (int64_t)__ldg(perm + r / block) * block + (r % block);
+    out[r * ldout + c] = __ldg(in + src * ldin + c);
+}
+
+}  // namespace rvgp
+
+using namespace rvgp;
+
+extern "C" int64_t rvgp_dgemm_workspace_bytes(int m, int n, int split_k) {
+    return split_k > 1 ? (int64_t)split_k * m * n * (int64_t)sizeof(double) : 0;
+}
+
+extern "C" int rvgp_dgemm_f64(rvgp_handle_t hh, int m, int n, int64_t k, double alpha, const double* A, int64_t lda,
+                              int a_kmajor, const double* B, int64_t ldb, int b_kmajor, const double* scale_k,
+                              double* C, int64_t ldc, int split_k, double* workspace) {
+    Handle* h = H(hh);
+    RVGP_REQUIRE(h, m >= 0 && n >= 0 && k >= 0 && split_k >= 1, "dgemm: bad sizes");
+    RVGP_REQUIRE(h, split_k == 1 || workspace != nullptr, "dgemm: split_k > 1 needs a workspace");
+    if (m == 0 || n == 0) return RVGP_OK;
+    dim3 grid(cdiv(n, BN), cdiv(m, BM), split_k);
+#define RVGP_GEMM(AK, BKM) dgemm_kernel<AK, BKM><<<grid, 256, 0, h->stream>>>(m, n, k, alpha, A, lda, B, ldb, scale_k, C, ldc, split_k, workspace)
+    if (a_kmajor && b_kmajor) RVGP_GEMM(true, true);
+    else if (a_kmajor && !b_kmajor) RVGP_GEMM(true, false);
+    else if (!a_kmajor && b_kmajor) RVGP_GEMM(false, true);
+    else RVGP_GEMM(false, false);
+#undef RVGP_GEMM
+    RVGP_LAUNCH_OK(h, "dgemm_kernel");
+    if (split_k > 1) {
+        const int64_t tot = (int64_t)m * n;
+        splitk_reduce_kernel<<<cdiv(tot, 256), 256, 0, h->stream>>>(m, n, split_k, alpha, workspace, C, ldc);
+        RVGP_LAUNCH_OK(h, "splitk_reduce_kernel");
+    }
+    return RVGP_OK;
+}
+
+extern "C" int64_t rvgp_coldot_workspace_bytes(int64_t nrows, int ncols) {
+    return (int64_t)cdiv(nrows, RED_ROWS_PER_CTA) * ncols * (int64_t)sizeof(double);
+}
+
+static int colreduce(Handle* h, int mode, int64_t nrows, int ncols, const double* A, int64_t lda, const double* B,
+                     int64_t ldb, const double* theta, double* out, double* ws) {
+    RVGP_REQUIRE(h, ncols >= 1 && nrows >= 0 && ws != nullptr, "colreduce: bad args");
+    const int nslabs = cdiv(nrows, RED_ROWS_PER_CTA);
+    if (nslabs > 0) {
+        if (mode == 0) colreduce_stage1<0><<<nslabs, 256, 0, h->stream>>>(nrows, ncols, A, lda, B, ldb, theta, ws);
+        else colreduce_stage1<1><<<nslabs, 256, 0, h->stream>>>(nrows, ncols, A, lda, B, ldb, theta, ws);
+        RVGP_LAUNCH_OK(h, "colreduce_stage1");
+    }
+    colreduce_stage2<<<cdiv(ncols, 128), 128, 0, h->stream>>>(nslabs, ncols, ws, out);
+    RVGP_LAUNCH_OK(h, "colreduce_stage2");
+    return RVGP_OK;
+}
+
+extern "C" int rvgp_coldot_f64(rvgp_handle_t hh, int64_t nrows, int ncols, const double* A, int64_t lda,
+                               const double* B, int64_t ldb, double* out, double* workspace) {
+    return colreduce(H(hh), 0, nrows, ncols, A, lda, B, ldb, nullptr, out, workspace);
+}
+
+extern "C" int rvgp_resid_sq_f64(rvgp_handle_t hh, int64_t nrows, int ncols, const double* W, int64_t ldw,
+                                 const double* V, int64_t ldv, const double* theta, double* out, double* workspace) {
+    return colreduce(H(hh), 1, nrows, ncols, W, ldw, V, ldv, theta, out, workspace);
+}
+
+extern "C" int rvgp_colscale_f64(rvgp_handle_t hh, int64_t nrows, int ncols, double* A, int64_t lda, const double* s) {
+    Handle* h = H(hh);
+    const int64_t tot = nrows * ncols;
+    if (tot == 0) return RVGP_OK;
+    colscale_kernel<<<cdiv(tot, 256), 256, 0, h->stream>>>(nrows, ncols, A, lda, s);
+    RVGP_LAUNCH_OK(h, "colscale_kernel");
+    return RVGP_OK;
+}
+
+extern "C" int rvgp_fill_uniform_f64(rvgp_handle_t hh, int64_t nrows, int ncols, double* A, int64_t lda, uint64_t seed,
+                                     int64_t col_offset) {
+    Handle* h = H(hh);
+    const int64_t tot = nrows * ncols;
+    if (tot == 0) return RVGP_OK;
+    fill_uniform_kernel<<<cdiv(tot, 256), 256, 0, h->stream>>>(nrows, ncols, A, lda, seed, col_offset);
+    RVGP_LAUNCH_OK(h, "fill_uniform_kernel");
+    return RVGP_OK;
+}
+
+extern "C" int rvgp_gather_rows_f64(rvgp_handle_t hh, int64_t nrows, int ncols, const double* in, int64_t ldin,
+                                    const int32_t* perm, int block, double* out, int64_t ldout) {
+    Handle* h = H(hh);
+    const int64_t tot = nrows * ncols;
+    if (tot == 0) return RVGP_OK;
+    gather_rows_kernel<<<cdiv(tot, 256), 256, 0, h->stream>>>(nrows, ncols, in, ldin, perm, block, out, ldout);
+    RVGP_LAUNCH_OK(h, "gather_rows_kernel");
+    return RVGP_OK;
+}

@@ -1,0 +1,245 @@
+"""Smallest-k eigenpairs of the (connection) Laplacian on the GPU.
+
+Replaces ``scipy.sparse.linalg.eigsh(A, k, which="SM")`` = ARPACK (reference RVGP/geometry.py:66-80).
+Method: Chebyshev-filtered subspace iteration (block method, so the exactly paired eigenvalues of
+``Lc`` on orientable 2-manifolds are handled as a block).  The hot loop is the fused block-SpMM
+``rvgp_cheb_filter_f64`` (one launch per polynomial degree per column panel); orthogonalisation and
+Rayleigh-Ritz use the FP64 ``rvgp_dgemm_f64`` kernel.  Only the m x m projected problems
+(m = k + buffer <= a few hundred) are factorised on the host with LAPACK, in the same way ARPACK itself
+hands its small tridiagonal/Hessenberg problems to LAPACK.
+
+All device memory is torch tensors; all device math is librvgp_b200.so.
+"""
+import math
+import time
+
+import numpy as np
+import torch
+
+from ._cabi import get_handle, I64, U64
+
+
+class BsrMatrix:
+    """Device block-CSR matrix with d x d FP64 blocks (vals None => unit-weight graph Laplacian pattern)."""
+
+    def __init__(self, nbrows, d, indptr, indices, vals=None, max_offdiag=None):
+        self.nbrows, self.d = int(nbrows), int(d)
+        self.indptr, self.indices, self.vals = indptr, indices, vals
+        self.nrows = self.nbrows * self.d
+        self.nnzb = int(indices.numel())
+        self.max_offdiag = max_offdiag   # max number of off-diagonal blocks in a row (Gershgorin)
+
+    def spmm_bytes(self, ncols, fused=False):
+        """Algorithmic HBM bytes of one SpMM launch (SURVEY.md 8d / DESIGN.md K9)."""
+        d = self.d
+        mat = self.nnzb * ((8 * d * d if self.vals is not None else 0) + 4) + 4 * (self.nbrows + 1)
+        return mat + 8 * self.nrows * ncols * (3 if fused else 2)
+
+    def spmm(self, X, Y, alpha=1.0, beta=0.0, gamma=0.0, W=None, h=None):
+        h = h or get_handle(X.device.index)
+        ncols = X.shape[1]
+        h.call("rvgp_bsr_spmm_f64", self.nbrows, self.d, self.indptr, self.indices, self.vals,
+               X, I64(X.stride(0)), W, I64(W.stride(0) if W is not None else 0), Y, I64(Y.stride(0)),
+               int(ncols), float(alpha), float(beta), float(gamma))
+        return Y
+
+    def matmat(self, X, out=None, h=None):
+        """out = A @ X for any number of columns (panels of <= 64)."""
+        if out is None:
+            out = torch.empty_like(X)
+        for c0 in range(0, X.shape[1], 64):
+            c1 = min(X.shape[1], c0 + 64)
+            self.spmm(X[:, c0:c1], out[:, c0:c1], h=h)
+        return out
+
+
+def _dgemm(h, m, n, k, A, lda, a_kmajor, B, ldb, b_kmajor, C, ldc, alpha=1.0, scale_k=None, split_k=1, ws=None):
+    h.call("rvgp_dgemm_f64", int(m), int(n), I64(k), float(alpha), A, I64(lda), int(a_kmajor), B, I64(ldb),
+           int(b_kmajor), scale_k, C, I64(ldc), int(split_k), ws)
+
+
+class _Dense:
+    """Tall-skinny FP64 products on (N x m) block vectors."""
+
+    def __init__(self, h, N, m, device):
+        self.h, self.N, self.m = h, N, m
+        tiles = math.ceil(m / 128) ** 2
+        self.split = max(1, min(64, (2 * h.sm_count) // tiles, N // 2048 if N >= 4096 else 1))
+        self.ws = torch.empty(self.split * m * m, dtype=torch.float64, device=device)
+        nred = h.query("rvgp_coldot_workspace_bytes", I64(N), int(m)) // 8
+        self.red_ws = torch.empty(max(1, nred), dtype=torch.float64, device=device)
+        self.small = torch.empty(m, dtype=torch.float64, device=device)
+
+    def gram(self, V, W, out):
+        """out (m1 x m2) = V^T W."""
+        m1, m2 = V.shape[1], W.shape[1]
+        _dgemm(self.h, m1, m2, self.N, V, V.stride(0), 0, W, W.stride(0), 0, out, out.stride(0),
+               split_k=self.split, ws=self.ws)
+        return out
+
+    def apply(self, V, Cm, out):
+        """out (N x m2) = V (N x m1) @ Cm (m1 x m2)."""
+        m1, m2 = Cm.shape
+        _dgemm(self.h, self.N, m2, m1, V, V.stride(0), 1, Cm, Cm.stride(0), 0, out, out.stride(0))
+        return out
+
+    def coldot(self, A, B):
+        out = self.small[: A.shape[1]]
+        self.h.call("rvgp_coldot_f64", I64(self.N), int(A.shape[1]), A, I64(A.stride(0)), B, I64(B.stride(0)),
+                    out, self.red_ws)
+        return out
+
+    def resid_sq(self, W, V, theta):
+        out = self.small[: V.shape[1]]
+        self.h.call("rvgp_resid_sq_f64", I64(self.N), int(V.shape[1]), W, I64(W.stride(0)), V, I64(V.stride(0)),
+                    theta, out, self.red_ws)
+        return out
+
+    def colscale(self, A, s):
+        self.h.call("rvgp_colscale_f64", I64(self.N), int(A.shape[1]), A, I64(A.stride(0)), s)
+
+
+def smallest_eigenpairs(A, k, upper_bound, lower_bound=0.0, tol=1e-12, nex=None, seed=0, max_outer=80,
+                        cond_max=1e7, deg0=20, panel=None, stats=None, verbose=False):
+    """Smallest k eigenpairs of the symmetric PSD BsrMatrix ``A``.
+
+    upper_bound: a rigorous upper bound of the spectrum (2 * max degree for (connection) Laplacians).
+    tol: residual tolerance relative to upper_bound, ||A x - theta x|| <= tol * upper_bound.
+    Returns (evals (k,) float64 cuda, evecs (N, k) float64 cuda, unit-norm columns, ascending).
+    """
+    dev = A.indptr.device
+    h = get_handle(dev.index)
+    N = A.nrows
+    k = int(min(k, N))
+    if nex is None:
+        nex = max(16, int(math.ceil(0.2 * k)))
+    m = min(N, k + nex)
+    if panel is None:
+        panel = 64 if m >= 128 else 32
+    if m < N:
+        m = min(N, ((m + panel - 1) // panel) * panel)
+    hi = float(upper_bound)
+    lo_spec = float(lower_bound)
+    tol_abs = tol * hi
+    st = stats if stats is not None else {}
+    st.update(dict(N=N, k=k, m=m, panel=panel, spmm_launches=0, filter_col_degrees=0, outer=0,
+                   t_filter=0.0, t_dense=0.0, t_host=0.0))
+
+    B1 = torch.empty((N, m), dtype=torch.float64, device=dev)
+    B2 = torch.empty((N, m), dtype=torch.float64, device=dev)
+    w0 = torch.empty((N, panel), dtype=torch.float64, device=dev)
+    w1 = torch.empty((N, panel), dtype=torch.float64, device=dev)
+    Gd = torch.empty((m, m), dtype=torch.float64, device=dev)
+    Hd = torch.empty((m, m), dtype=torch.float64, device=dev)
+    Cd = torch.empty((m, m), dtype=torch.float64, device=dev)
+    theta_d = torch.empty(m, dtype=torch.float64, device=dev)
+    dense = _Dense(h, N, m, dev)
+
+    V, W = B1, B2
+    h.call("rvgp_fill_uniform_f64", I64(N), int(m), V, I64(V.stride(0)), U64(seed), I64(0))
+
+    deg = np.full(m, deg0, dtype=np.int64)
+    a_cut = lo_spec + 0.3 * (hi - lo_spec)
+    theta = res = None
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    ev2 = torch.cuda.Event(enable_timing=True)
+
+    for it in range(max_outer):
+        ev0.record()
+        # ---- polynomial filter: one fused SpMM launch per degree per panel -------------------------
+        for p0 in range(0, m, panel):
+            p1 = min(m, p0 + panel)
+            dg = int(deg[p0:p1].max())
+            if dg <= 0:
+                continue
+            Vp = V[:, p0:p1]
+            h.call("rvgp_cheb_filter_f64", A.nbrows, A.d, A.indptr, A.indices, A.vals, Vp, I64(V.stride(0)),
+                   w0, w1, I64(panel), int(p1 - p0), dg, lo_spec, float(a_cut), hi)
+            st["spmm_launches"] += dg
+            st["filter_col_degrees"] += dg * (p1 - p0)
+        ev1.record()
+        # ---- orthonormalise: column scaling + Cholesky-QR, then Rayleigh-Ritz with the second
+        #      Cholesky folded into the projected problem ---------------------------------------------
+        nrm = dense.coldot(V, V)
+        inv = torch.rsqrt(nrm)
+        dense.colscale(V, inv)
+        dense.gram(V, V, Gd)
+        t0 = time.perf_counter()
+        G = Gd.cpu().numpy()
+        G = 0.5 * (G + G.T)
+        R = np.linalg.cholesky(G).T                       # G = R^T R
+        Rinv = _tri_inv_upper(R)
+        st["t_host"] += time.perf_counter() - t0
+        Cd.copy_(torch.from_numpy(np.ascontiguousarray(Rinv)))
+        dense.apply(V, Cd, W)                              # W = V R^-1   (nearly orthonormal)
+        V, W = W, V
+        A.matmat(V, out=W, h=h)                            # W = A V
+        st["spmm_launches"] += math.ceil(m / 64)
+        dense.gram(V, V, Gd)
+        dense.gram(V, W, Hd)
+        t0 = time.perf_counter()
+        G = Gd.cpu().numpy(); G = 0.5 * (G + G.T)
+        Hm = Hd.cpu().numpy(); Hm = 0.5 * (Hm + Hm.T)
+        R2 = np.linalg.cholesky(G).T
+        R2inv = _tri_inv_upper(R2)
+        Hm = R2inv.T @ Hm @ R2inv
+        Hm = 0.5 * (Hm + Hm.T)
+        theta, Y = np.linalg.eigh(Hm)
+        Cm = R2inv @ Y
+        st["t_host"] += time.perf_counter() - t0
+        Cd.copy_(torch.from_numpy(np.ascontiguousarray(Cm)))
+        theta_d.copy_(torch.from_numpy(theta))
+        dense.apply(V, Cd, W)                              # Ritz vectors
+        V, W = W, V
+        A.matmat(V, out=W, h=h)                            # A * Ritz vectors, for true residuals
+        st["spmm_launches"] += math.ceil(m / 64)
+        res = torch.sqrt(dense.resid_sq(W, V, theta_d)).cpu().numpy()
+        ev2.record()
+        torch.cuda.synchronize(dev)
+        st["t_filter"] += ev0.elapsed_time(ev1) * 1e-3
+        st["t_dense"] += ev1.elapsed_time(ev2) * 1e-3
+        st["outer"] = it + 1
+
+        nconv = int((res[:k] <= tol_abs).sum())
+        a_cut = float(theta[-1]) if m < N else a_cut
+        if verbose:
+            print("  [eig] it %d  cut=%.6g  conv=%d/%d  maxres=%.3e  theta_k=%.9g" %
+                  (it, a_cut, nconv, k, res[:k].max(), theta[k - 1]))
+        if nconv == k or m >= N:
+            break
+        a_cut = max(a_cut, lo_spec + 1e-12 * (hi - lo_spec) + theta[k - 1] * (1 + 1e-9))
+        deg = _next_degrees(theta, res, k, tol_abs, a_cut, hi, lo_spec, cond_max)
+
+    st["residual_max"] = float(res[:k].max())
+    st["converged"] = bool((res[:k] <= tol_abs).all())
+    evals = theta_d[:k].clone()
+    evecs = V[:, :k]
+    return evals, evecs
+
+
+def _tri_inv_upper(R):
+    import scipy.linalg
+    return scipy.linalg.solve_triangular(R, np.eye(R.shape[0]), lower=False)
+
+
+def _next_degrees(theta, res, k, tol_abs, a_cut, hi, lo_spec, cond_max, deg_cap=6000):
+    """Per-column Chebyshev degree for the next sweep (ChASE-style degree optimisation).
+
+    Column i with Ritz value theta_i is amplified by exp(g_i) per degree relative to the damped interval
+    [a_cut, hi], g_i = acosh((c - theta_i)/e).  The degree is what brings its residual a decade below
+    tol, capped so the filtered block stays numerically full rank (relative growth of the lowest
+    eigen-direction <= cond_max)."""
+    e = 0.5 * (hi - a_cut)
+    c = 0.5 * (hi + a_cut)
+    g = np.arccosh(np.maximum((c - theta) / e, 1.0))
+    g0 = math.acosh(max((c - lo_spec) / e, 1.0))
+    with np.errstate(divide="ignore"):
+        need = np.where(res > tol_abs,
+                        np.maximum(np.log(np.maximum(10.0 * res / tol_abs, 1.0)) / np.maximum(g, 1e-12), 8.0), 0.0)
+    cap = math.log(cond_max) / np.maximum(g0 - g, 1e-12)
+    d = np.ceil(np.minimum(need * 1.05 + 1.0, cap))
+    d[res <= tol_abs] = 0
+    if k < len(d):
+        d[k:] = np.minimum(d[k:], d[:k].max())
+    return np.minimum(d, deg_cap).astype(np.int64)

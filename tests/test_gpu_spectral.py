@@ -1,0 +1,160 @@
+"""GPU parity tests (through the C-ABI) for K9 block-SpMM, K10 dense kernels and the eigensolver."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+from tests.conftest import load_golden, subspace_angle_max, eigen_clusters
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    return torch.device("cuda", 0)
+
+
+def _bsr_from_golden(g, which="Lc"):
+    from rvgp_b200.eigensolver import BsrMatrix
+    n = g["X"].shape[0]
+    if which == "Lc":
+        d = int(g["dim_man"])
+        vals = torch.from_numpy(g["Lc_data"]).to(_dev())
+        A = BsrMatrix(n, d, torch.from_numpy(g["Lc_indptr"]).to(_dev()), torch.from_numpy(g["Lc_indices"]).to(_dev()), vals)
+        S = sp.bsr_matrix((g["Lc_data"], g["Lc_indices"], g["Lc_indptr"]), shape=(n * d, n * d)).tocsr()
+    else:
+        A = BsrMatrix(n, 1, torch.from_numpy(g["L_indptr"]).to(_dev()), torch.from_numpy(g["L_indices"]).to(_dev()), None)
+        S = sp.csr_matrix((g["L_data"], g["L_indices"], g["L_indptr"]), shape=(n, n))
+    return A, S
+
+
+@pytest.mark.parametrize("case", ["sphere_n2000_k50", "flat3torus_R6_n900_k24", "sheet_R20_n500_k16"])
+@pytest.mark.parametrize("ncols", [1, 7, 16, 32, 50, 64])
+def test_spmm_matches_scipy(case, ncols):
+    g = load_golden(case)
+    for which in ("Lc", "L"):
+        A, S = _bsr_from_golden(g, which)
+        rng = np.random.default_rng(1)
+        X = rng.normal(size=(A.nrows, ncols))
+        W = rng.normal(size=(A.nrows, ncols))
+        Xd, Wd = torch.from_numpy(X).to(_dev()), torch.from_numpy(W).to(_dev())
+        Yd = torch.empty_like(Xd)
+        A.spmm(Xd, Yd)
+        ref = S @ X
+        assert np.abs(Yd.cpu().numpy() - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max())
+        A.spmm(Xd, Yd, alpha=0.7, beta=-1.3, gamma=0.25, W=Wd)
+        ref2 = 0.7 * ref - 1.3 * X + 0.25 * W
+        assert np.abs(Yd.cpu().numpy() - ref2).max() <= 1e-13 * max(1.0, np.abs(ref2).max())
+
+
+def test_spmm_strided_and_empty():
+    g = load_golden("torus_n600_k20")
+    A, S = _bsr_from_golden(g, "Lc")
+    big = torch.zeros((A.nrows, 96), dtype=torch.float64, device=_dev())
+    X = np.random.default_rng(0).normal(size=(A.nrows, 20))
+    big[:, 10:30] = torch.from_numpy(X).to(_dev())
+    out = torch.zeros((A.nrows, 40), dtype=torch.float64, device=_dev())
+    A.spmm(big[:, 10:30], out[:, 5:25])
+    assert np.abs(out[:, 5:25].cpu().numpy() - S @ X).max() < 1e-12
+    assert out[:, :5].abs().max().item() == 0.0 and out[:, 25:].abs().max().item() == 0.0
+    with pytest.raises(ValueError):
+        A.spmm(big[:, :65], torch.empty((A.nrows, 65), dtype=torch.float64, device=_dev()))
+
+
+@pytest.mark.parametrize("degree", [1, 2, 3, 7, 30])
+def test_cheb_filter_matches_recurrence(degree):
+    from rvgp_b200._cabi import get_handle, I64
+    g = load_golden("torus_n600_k20")
+    A, S = _bsr_from_golden(g, "Lc")
+    X = np.random.default_rng(3).normal(size=(A.nrows, 24))
+    hi, cut, lo = 40.0, 1.5, 0.0
+    e, c = (hi - cut) / 2, (hi + cut) / 2
+    s1 = e / (lo - c); tau = 2 / s1; sg = s1
+    Xp, Y = X, (S @ X - c * X) * (s1 / e)
+    for i in range(2, degree + 1):
+        sn = 1 / (tau - sg)
+        Xp, Y, sg = Y, (S @ Y - c * Y) * (2 * sn / e) - sg * sn * Xp, sn
+    V = torch.from_numpy(X).to(_dev())
+    w0 = torch.empty((A.nrows, 32), dtype=torch.float64, device=_dev()); w1 = torch.empty_like(w0)
+    h = get_handle(0)
+    h.call("rvgp_cheb_filter_f64", A.nbrows, A.d, A.indptr, A.indices, A.vals, V, I64(V.stride(0)), w0, w1, I64(32),
+           24, degree, lo, cut, hi)
+    assert np.abs(V.cpu().numpy() - Y).max() <= 1e-12 * np.abs(Y).max()
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 5), (37, 53, 1000), (200, 129, 4097), (256, 256, 70000), (130, 7, 333)])
+def test_dgemm_layouts(shape):
+    from rvgp_b200.eigensolver import _dgemm
+    from rvgp_b200._cabi import get_handle
+    m, n, k = shape
+    h = get_handle(0)
+    rng = np.random.default_rng(0)
+    for akm in (0, 1):
+        for bkm in (0, 1):
+            for split in (1, 5):
+                A = rng.normal(size=(m, k)); B = rng.normal(size=(k, n)); s = rng.uniform(0.5, 2, size=k)
+                Ad = torch.from_numpy(np.ascontiguousarray(A if akm else A.T)).to(_dev())
+                Bd = torch.from_numpy(np.ascontiguousarray(B.T if bkm else B)).to(_dev())
+                sd = torch.from_numpy(s).to(_dev())
+                C = torch.zeros((m, n + 3), dtype=torch.float64, device=_dev())
+                ws = torch.empty(split * m * n, dtype=torch.float64, device=_dev())
+                _dgemm(h, m, n, k, Ad, Ad.stride(0), akm, Bd, Bd.stride(0), bkm, C, C.stride(0), alpha=0.5,
+                       scale_k=sd, split_k=split, ws=ws)
+                ref = 0.5 * (A * s) @ B
+                err = np.abs(C[:, :n].cpu().numpy() - ref).max()
+                assert err <= 1e-13 * k ** 0.5 * max(1, np.abs(ref).max()), (akm, bkm, split, err)
+                assert C[:, n:].abs().max().item() == 0.0
+
+
+def test_column_reductions_and_utils():
+    from rvgp_b200._cabi import get_handle, I64, U64
+    h = get_handle(0)
+    N, m = 10007, 77
+    rng = np.random.default_rng(0)
+    A = rng.normal(size=(N, m)); B = rng.normal(size=(N, m)); th = rng.normal(size=m)
+    Ad, Bd, thd = (torch.from_numpy(x).to(_dev()) for x in (A, B, th))
+    ws = torch.empty(h.query("rvgp_coldot_workspace_bytes", I64(N), m) // 8, dtype=torch.float64, device=_dev())
+    out = torch.empty(m, dtype=torch.float64, device=_dev())
+    h.call("rvgp_coldot_f64", I64(N), m, Ad, I64(m), Bd, I64(m), out, ws)
+    np.testing.assert_allclose(out.cpu().numpy(), (A * B).sum(0), rtol=1e-12, atol=1e-10)
+    h.call("rvgp_resid_sq_f64", I64(N), m, Ad, I64(m), Bd, I64(m), thd, out, ws)
+    np.testing.assert_allclose(out.cpu().numpy(), ((A - th * B) ** 2).sum(0), rtol=1e-12)
+    h.call("rvgp_colscale_f64", I64(N), m, Ad, I64(m), thd)
+    np.testing.assert_allclose(Ad.cpu().numpy(), A * th, rtol=1e-15)
+    F1 = torch.empty((N, m), dtype=torch.float64, device=_dev()); F2 = torch.empty((N, 10), dtype=torch.float64, device=_dev())
+    h.call("rvgp_fill_uniform_f64", I64(N), m, F1, I64(m), U64(7), I64(0))
+    h.call("rvgp_fill_uniform_f64", I64(N), 10, F2, I64(10), U64(7), I64(20))
+    f1 = F1.cpu().numpy()
+    assert np.array_equal(f1[:, 20:30], F2.cpu().numpy())          # counter based: depends on (seed,row,col) only
+    assert abs(f1.mean()) < 0.01 and f1.min() >= -1 and f1.max() < 1 and abs(f1.std() - 3 ** -0.5) < 0.01
+    perm = torch.from_numpy(rng.permutation(N // 1).astype(np.int32)).to(_dev())
+    G = torch.empty_like(Bd)
+    h.call("rvgp_gather_rows_f64", I64(N), m, Bd, I64(m), perm, 1, G, I64(m))
+    assert np.array_equal(G.cpu().numpy(), B[perm.cpu().numpy()])
+
+
+@pytest.mark.parametrize("case", ["sphere_n2000_k50", "torus_n600_k20", "flat3torus_R6_n900_k24", "sheet_R20_n500_k16"])
+def test_eigensolver_matches_reference_arpack(case):
+    """Eigenvalues rel 1e-8 (absolute 1e-8*|L| for the zero mode), eigen-subspace angles < 1e-6 per cluster
+    against the golden ARPACK output of the unmodified reference (geometry.py:73)."""
+    from rvgp_b200.eigensolver import smallest_eigenpairs
+    g = load_golden(case)
+    k = len(g["evals_Lc"])
+    n = g["X"].shape[0]
+    d = int(g["dim_man"])
+    maxdeg = int(np.diff(g["indptr"]).max() - 1)
+    for which, ev_ref in (("Lc", g["evals_Lc"]), ("L", g["evals_L"])):
+        A, S = _bsr_from_golden(g, which)
+        st = {}
+        ev, U = smallest_eigenpairs(A, k, upper_bound=2.0 * maxdeg, stats=st)
+        ev = ev.cpu().numpy(); U = U.cpu().numpy()
+        assert st["converged"], st
+        np.testing.assert_allclose(ev, ev_ref, rtol=1e-8, atol=1e-8 * 2 * maxdeg)
+        assert np.abs(U.T @ U - np.eye(k)).max() < 1e-10
+        assert np.abs(S @ U - U * ev).max() < 1e-8
+        if which == "Lc":
+            Phi = np.einsum("bij,bjk->bik", g["gauges"], (U * np.sqrt(n * d)).reshape(n, d, k)).reshape(-1, k)
+            ref = g["evecs_Lc"]
+        else:
+            Phi, ref = U * np.sqrt(n), g["evecs_L"]
+        for s in eigen_clusters(ev_ref)[:-1]:
+            assert subspace_angle_max(Phi[:, s], ref[:, s]) < 1e-6, (which, s)

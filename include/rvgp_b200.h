@@ -76,10 +76,11 @@ int rvgp_dgemm_f64(rvgp_handle_t h, int m, int n, int64_t k, double alpha, const
 int64_t rvgp_dgemm_workspace_bytes(int m, int n, int split_k);
 
 /* column-wise reductions over tall block vectors (deterministic two-stage) ---------------------------
- * out[c] = sum_r A[r*lda+c] * B[r*ldb+c]           (ncols <= 1024).  workspace: rvgp_coldot_workspace_bytes */
+ * out[c] = sum_r A[r*lda+c] * B[r*ldb+c]   (B == NULL: B = 1, i.e. column sums).
+ * workspace: rvgp_coldot_workspace_bytes */
 int rvgp_coldot_f64(rvgp_handle_t h, int64_t nrows, int ncols, const double* A, int64_t lda,
                     const double* B, int64_t ldb, double* out, double* workspace);
-/* out[c] = sum_r (W[r,c] - theta[c] * V[r,c])^2    (squared residual norms of Ritz pairs) */
+/* out[c] = sum_r (W[r,c] - theta[c] * V[r,c])^2    (squared residual norms of Ritz pairs; V == NULL: V = 1) */
 int rvgp_resid_sq_f64(rvgp_handle_t h, int64_t nrows, int ncols, const double* W, int64_t ldw,
                       const double* V, int64_t ldv, const double* theta, double* out, double* workspace);
 int64_t rvgp_coldot_workspace_bytes(int64_t nrows, int ncols);
@@ -91,6 +92,68 @@ int rvgp_fill_uniform_f64(rvgp_handle_t h, int64_t nrows, int ncols, double* A, 
 /* out[r, c] = in[perm[r], c] for r < nrows (row gather; used for the locality permutation) */
 int rvgp_gather_rows_f64(rvgp_handle_t h, int64_t nrows, int ncols, const double* in, int64_t ldin,
                          const int32_t* perm, int block, double* out, int64_t ldout);
+
+/* ---- K2: exact kNN (replaces sklearn kneighbors_graph, geometry.py:103-110) -------------------------
+ * X (n, D) all candidates; queries are rows [q_begin, q_begin+q_count) (row sharding across GPUs).
+ * out_idx (q_count, k) int32 in ascending (distance, index) order, self excluded by index;
+ * out_d2 (nullable) squared distances.  Distances are sum_j (x_j-y_j)^2 in coordinate order, no FMA. */
+int rvgp_knn_f64(rvgp_handle_t h, const double* X, int n, int D, int q_begin, int q_count, int k,
+                 int32_t* out_idx, double* out_d2);
+
+/* ---- K3: kNN lists -> symmetric CSR with self loops (geometry.py:111-112, ptu_dijkstra.pyx:84-103) ----- */
+int rvgp_knn_to_csr(rvgp_handle_t h, const int32_t* knn, int n, int k, int32_t* indptr, int32_t* indices,
+                    int32_t* nnz_out, void* workspace, int64_t workspace_bytes);
+int64_t rvgp_knn_to_csr_workspace_bytes(int n, int k);
+/* locality (Morton) ordering of the points and symmetric permutation of a CSR pattern (eigensolver layout) */
+int rvgp_morton_order(rvgp_handle_t h, const double* X, int n, int D, int32_t* order, int32_t* inv,
+                      void* workspace, int64_t workspace_bytes);
+int64_t rvgp_morton_order_workspace_bytes(int n);
+int rvgp_csr_permute(rvgp_handle_t h, int n, const int32_t* indptr, const int32_t* indices, const int32_t* order,
+                     const int32_t* inv, int32_t* new_indptr, int32_t* new_indices, void* workspace,
+                     int64_t workspace_bytes);
+int64_t rvgp_csr_permute_workspace_bytes(int n);
+
+/* ---- K4: geodesic neighbourhoods = literal Fibonacci-heap Dijkstra (ptu_dijkstra.pyx:361-394, 444-690) --
+ * seq (n, K+1) popped ids in pop order; counts (n); flags: device int32 (bit0 short component -> stale tail
+ * reproduced, bit1 decrease_val would have fired, bit2 node-pool overflow). */
+int rvgp_geodesic_neighbourhoods(rvgp_handle_t h, const int32_t* indptr, const int32_t* indices, int n, int K,
+                                 int maxdeg, int32_t* seq, int32_t* counts, int32_t* flags, void* workspace,
+                                 int64_t workspace_bytes);
+int64_t rvgp_geodesic_workspace_bytes(rvgp_handle_t h, int n, int K, int maxdeg);
+
+/* ---- K5/K6: tangent frames (ptu_dijkstra.pyx:396-434) and dimension statistic (geometry.py:83-97) ------ */
+int rvgp_tangent_frames(rvgp_handle_t h, const double* X, int n, int D, const int32_t* seq, int Kp1, int dcheck,
+                        double* tangents, double* Sigma, int32_t* flag);
+int rvgp_sigma_cumvar(rvgp_handle_t h, const double* Sigma, int n, int D, double* cum);
+int rvgp_slice_frames(rvgp_handle_t h, const double* T, int64_t n, int D, int dfull, int d, double* G);
+
+/* ---- K7/K8: Procrustes connections + connection-Laplacian assembly (ptu_dijkstra.pyx:259-293,
+ * geometry.py:35-42).  For every stored CSR entry e=(i,j) incl. the diagonal: R = U V^T of svd(T_i^T T_j);
+ * Lc block = deg_i * R on the diagonal entry, -R elsewhere (deg_i = row length - 1).
+ * gauges (n, D, d); Lc_vals, R_vals (each nullable): (nnzb, d, d) in CSR entry order. */
+int rvgp_connections(rvgp_handle_t h, const double* gauges, int n, int D, int d, const int32_t* indptr,
+                     const int32_t* indices, int64_t nnzb, double* Lc_vals, double* R_vals);
+
+/* ---- K11/a15: frame contractions ------------------------------------------------------------------------
+ * mode 0: out(n,d)   = G^T x      express_in_local_frame          (geometry.py:171-176)
+ * mode 1: out(n,D)   = G x        express_in_local_frame(reverse) / eigenvector lift (dataclass.py:57-59)
+ * x and out carry `ncols` trailing columns: x (n, d|D, ncols), out (n, D|d, ncols). */
+int rvgp_frame_apply(rvgp_handle_t h, const double* gauges, int64_t n, int D, int d, const double* x, double* out,
+                     int ncols, int mode, double scale);
+
+/* ---- K1: furthest-point sampling (geometry.py:126-162), one persistent cooperative kernel ---------------
+ * N > 0: exactly N samples; N == 0: until lambdas[i]/diam < spacing (diam = max pairwise distance, computed
+ * here with sklearn's euclidean_distances expansion).  perm/lambdas capacity: N, or n when N == 0. */
+int rvgp_fps_f64(rvgp_handle_t h, const double* X, int n, int D, int N, double spacing, int start_idx,
+                 int32_t* perm, double* lambdas, int32_t* count_out, void* workspace, int64_t workspace_bytes);
+int64_t rvgp_fps_workspace_bytes(rvgp_handle_t h, int n);
+
+/* ---- K12 helpers: vector-diffusion smoothing (smoothing.py:37-64), random field (dataclass.py:91-103) ---
+ * Y += a X ; out[i] = ||x[i,:]|| ; x[i,:] *= out_abs[i] / (ind[i] * ||x[i,:]||)  (out_abs/ind nullable = 1) */
+int rvgp_axpy_f64(rvgp_handle_t h, int64_t nrows, int ncols, double a, const double* X, int64_t ldx, double* Y,
+                  int64_t ldy);
+int rvgp_row_norms_f64(rvgp_handle_t h, int64_t n, int d, const double* x, double* out);
+int rvgp_renorm_rows_f64(rvgp_handle_t h, int64_t n, int d, double* x, const double* out_abs, const double* ind);
 
 #ifdef __cplusplus
 }

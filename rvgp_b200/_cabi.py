@@ -51,8 +51,9 @@ def load_library():
             lib = ctypes.CDLL(LIB_PATH)
             lib.rvgp_last_error.restype = ctypes.c_char_p
             lib.rvgp_launch_count.restype = ctypes.c_ulonglong
-            for name in ("rvgp_dgemm_workspace_bytes", "rvgp_coldot_workspace_bytes"):
-                getattr(lib, name).restype = ctypes.c_int64
+            for name in declared_symbols():
+                if name.endswith("_workspace_bytes"):
+                    getattr(lib, name).restype = ctypes.c_int64
             _lib = lib
     return _lib
 

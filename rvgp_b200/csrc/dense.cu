@@ -150,7 +150,7 @@ colreduce_stage1(int64_t nrows, int ncols, const double* __restrict__ A, int64_t
         if (c < ncols) {
             const double th = (MODE == 1) ? __ldg(theta + c) : 0.0;
             for (int64_t r = r0 + ry; r < r1; r += 8) {
-                const double a = __ldg(A + r * lda + c), b = __ldg(B + r * ldb + c);
+                const double a = __ldg(A + r * lda + c), b = B ? __ldg(B + r * ldb + c) : 1.0;
                 if (MODE == 0) s = fma(a, b, s);
                 else { const double d = a - th * b; s = fma(d, d, s); }
             }

@@ -1,0 +1,289 @@
+"""The data object: mirror of the reference's ``RVGP/dataclass.py`` (class ``data``, exported as
+``RVGP.create_data_object``, RVGP/__init__.py:2) with every stage on the GPU.
+
+Pipeline (dataclass.py:22-89): kNN graph -> geodesic-neighbourhood tangent frames -> manifold dimension ->
+connections -> L, Lc -> smallest-k spectra of both -> ambient lift of the Lc eigenvectors.
+
+Attributes keep the reference's names and host types (numpy / scipy / networkx) but are materialised lazily
+from device-resident results on first access: building a 12 M-edge networkx graph or copying a 12 GB
+eigenvector matrix to the host eagerly would cost more than the whole GPU pipeline.  Assigning to an attribute
+(examples overwrite ``d.vectors``, ``d.evals_Lc``, ``d.evecs_Lc``) replaces the value for every later consumer.
+"""
+import time
+
+import numpy as np
+import torch
+
+from . import geometry as geo
+from .eigensolver import BsrMatrix, smallest_eigenpairs
+from .smoothing import vector_diffusion_device
+
+
+class _Dual:
+    """A value that lives on the device, on the host, or both."""
+
+    def __init__(self, dev=None, host=None, to_host=None):
+        self.dev, self.host, self._to_host = dev, host, to_host
+
+    def get_host(self):
+        if self.host is None:
+            self.host = self._to_host(self.dev) if self._to_host else self.dev.cpu().numpy()
+        return self.host
+
+    def get_dev(self, device):
+        if self.dev is None:
+            self.dev = geo.to_device_f64(self.host, device)
+        return self.dev
+
+
+def _dual_property(name):
+    def fget(self):
+        return self._duals[name].get_host()
+
+    def fset(self, value):
+        if isinstance(value, torch.Tensor) and value.is_cuda:
+            self._duals[name] = _Dual(dev=value)
+        else:
+            self._duals[name] = _Dual(host=value)
+
+    return property(fget, fset)
+
+
+class data:
+    def __init__(self,
+                 vertices,
+                 vectors=None,
+                 dim_man=2,
+                 n_neighbors=10,
+                 frac_geodesic_neighbours=1.5,
+                 explained_variance=0.8,
+                 n_eigenpairs=None,
+                 device=None,
+                 eig_tol=1e-12,
+                 verbose=True):
+        say = print if verbose else (lambda *a, **k: None)
+        self._duals = {}
+        self.timings = {}
+        self.stats = {}
+        dev = geo._dev(device)
+        self.device = dev
+
+        def tick():
+            torch.cuda.synchronize(dev)
+            return time.perf_counter()
+
+        t0 = tick()
+        Xd = geo.to_device_f64(vertices, dev)
+        n, D = Xd.shape
+        self.timings["h2d"] = tick() - t0
+
+        say('Fit graph')
+        t0 = tick()
+        graph = geo.manifold_graph(Xd, n_neighbors=n_neighbors, device=dev)
+        self.timings["graph"] = tick() - t0
+
+        say('Fit tangent spaces')
+        t0 = tick()
+        # ptu_dijkstra.tangent_frames(vertices, G, d=D, K=n_neighbors*frac)  (dataclass.py:35; K truncated to int)
+        K = n_neighbors * frac_geodesic_neighbours
+        if K >= n:
+            raise ValueError("Geodesic neighborhood size must be less than the total number of samples")
+        if K < D:
+            raise ValueError("Geodesic neighborhood size must be larger or equal to the embedding dimension")
+        max_row = graph.max_row
+        seq, _ = geo.geodesic_neighbourhoods_device(graph.indptr, graph.indices, int(K), max_row)
+        self.timings["geodesic"] = tick() - t0
+        t0 = tick()
+        tangents, Sigma = geo.tangent_frames_device(Xd, seq, D)
+        if explained_variance == 1.0:
+            dim_man = D
+        else:
+            var_exp = geo.explained_variance_device(Sigma)
+            say("Fraction of variance explained: ", var_exp)
+            dim_man = int(np.where(var_exp >= explained_variance)[0][0] + 1)
+        gauges = geo.slice_frames_device(tangents, dim_man)
+        del tangents
+        say('Predicted manifold dimension is {}'.format(dim_man))
+        self.timings["tangent_frames"] = tick() - t0
+
+        # locality ordering for the spectral stage (the heap emulation above needed the ORIGINAL numbering)
+        t0 = tick()
+        order, inv = geo.morton_order_device(Xd)
+        p_indptr, p_indices = geo.csr_permute_device(graph.indptr, graph.indices, order, inv)
+        gauges_p = geo.gather_rows_device(gauges.reshape(n, D * dim_man), order).reshape(n, D, dim_man)
+        self.timings["reorder"] = tick() - t0
+
+        t0 = tick()
+        Lc_vals_p = geo.connections_device(gauges_p, p_indptr, p_indices)
+        say('Fit connections')
+        say('Compute Laplacians')
+        A_Lc = BsrMatrix(n, dim_man, p_indptr, p_indices, Lc_vals_p)
+        A_L = BsrMatrix(n, 1, p_indptr, p_indices, None)
+        self.timings["connections"] = tick() - t0
+
+        say('Compute eigendecompositions')
+        N_L, N_Lc = n, n * dim_man
+        k_L = N_L if (n_eigenpairs is None or n_eigenpairs >= N_L) else n_eigenpairs
+        k_Lc = N_Lc if (n_eigenpairs is None or n_eigenpairs >= N_Lc) else n_eigenpairs
+        hi = 2.0 * (max_row - 1)
+        t0 = tick()
+        st_L = {}
+        evals_L, U_L_p = smallest_eigenpairs(A_L, k_L, upper_bound=hi, tol=eig_tol, stats=st_L)
+        self.timings["eig_L"] = tick() - t0
+        t0 = tick()
+        st_Lc = {}
+        evals_Lc, U_Lc_p = smallest_eigenpairs(A_Lc, k_Lc, upper_bound=hi, tol=eig_tol, stats=st_Lc)
+        self.timings["eig_Lc"] = tick() - t0
+        self.stats["eig_L"], self.stats["eig_Lc"] = st_L, st_Lc
+
+        t0 = tick()
+        # un-permute; scale by sqrt(#rows) (geometry.py:75); lift T u to ambient coordinates (dataclass.py:57-59)
+        evecs_L = geo.gather_rows_device(U_L_p.contiguous(), inv)
+        h = geo.get_handle(dev.index)
+        kk = evecs_L.shape[1]
+        sc = torch.full((kk,), float(np.sqrt(N_L)), dtype=torch.float64, device=dev)
+        h.call("rvgp_colscale_f64", geo.I64(N_L), int(kk), evecs_L, geo.I64(evecs_L.stride(0)), sc)
+        kc = U_Lc_p.shape[1]
+        lifted_p = geo.frame_apply_device(gauges_p, U_Lc_p.contiguous().reshape(n, dim_man, kc), 1, scale=float(np.sqrt(N_Lc)))
+        evecs_Lc = geo.gather_rows_device(lifted_p.reshape(n * D, kc), inv, block=D)
+        del lifted_p
+        self.timings["lift"] = tick() - t0
+
+        # device-resident state used by smooth_vector_field / fit
+        self._graph = graph
+        self._Xd = Xd
+        self._perm = (order, inv)
+        self._A_Lc_p, self._A_L_p = A_Lc, A_L
+        self._U_Lc_p, self._U_L_p = U_Lc_p, U_L_p           # unit-norm, permuted row order
+        self._evals_Lc_d, self._evals_L_d = evals_Lc, evals_L
+        self._gauges_p = gauges_p
+        self._hi = hi
+
+        self.vertices = vertices
+        self.n = n
+        self.dim_man = dim_man
+        self.gauges = gauges
+        self.evals_L = evals_L
+        self.evecs_L = evecs_L
+        self.evals_Lc = evals_Lc
+        self.evecs_Lc = evecs_Lc
+        self.vectors = vectors
+        self._lazy = {}
+
+    # dual-resident numeric attributes (host numpy on access, device tensor for the kernels)
+    gauges = _dual_property("gauges")
+    evals_L = _dual_property("evals_L")
+    evecs_L = _dual_property("evecs_L")
+    evals_Lc = _dual_property("evals_Lc")
+    evecs_Lc = _dual_property("evecs_Lc")
+
+    @property
+    def vectors(self):
+        v = self._duals.get("vectors")
+        return None if v is None else v.get_host()
+
+    @vectors.setter
+    def vectors(self, value):
+        if value is None:
+            self._duals.pop("vectors", None)
+        elif isinstance(value, torch.Tensor) and value.is_cuda:
+            self._duals["vectors"] = _Dual(dev=value)
+        else:
+            self._duals["vectors"] = _Dual(host=np.asarray(value))
+
+    def device_array(self, name):
+        """Device tensor of a dual attribute (uploads a user-assigned host value on first use)."""
+        return self._duals[name].get_dev(self.device)
+
+    # host-object attributes of the reference, built on first access --------------------------------------
+    @property
+    def G(self):
+        if "G" not in self._lazy:
+            self._lazy["G"] = self._graph.to_networkx()
+        return self._lazy["G"]
+
+    @G.setter
+    def G(self, value):
+        self._lazy["G"] = value
+
+    @property
+    def L(self):
+        if "L" not in self._lazy:
+            self._lazy["L"] = geo.compute_laplacian(self._graph)
+        return self._lazy["L"]
+
+    @L.setter
+    def L(self, value):
+        self._lazy["L"] = value
+
+    def _R_blocks(self):
+        if "Rb" not in self._lazy:
+            g = self.device_array("gauges")
+            Lc, R = geo.connections_device(g, self._graph.indptr, self._graph.indices, want_R=True)
+            self._lazy["Rb"] = (Lc.cpu().numpy(), R.cpu().numpy())
+        return self._lazy["Rb"]
+
+    @property
+    def R(self):
+        """scipy COO (nd x nd) of the connection blocks in CSR entry order (ptu_dijkstra.pyx:194-197)."""
+        if "R" not in self._lazy:
+            from scipy import sparse
+            d = self.dim_man
+            _, Rb = self._R_blocks()
+            ip = self._graph.indptr.cpu().numpy()
+            ix = self._graph.indices.cpu().numpy()
+            B = sparse.bsr_matrix((Rb, ix, ip), shape=(self.n * d, self.n * d))
+            self._lazy["R"] = B.tocoo()
+        return self._lazy["R"]
+
+    @R.setter
+    def R(self, value):
+        self._lazy["R"] = value
+
+    @property
+    def Lc(self):
+        if "Lc" not in self._lazy:
+            from scipy import sparse
+            d = self.dim_man
+            Lcb, _ = self._R_blocks()
+            ip = self._graph.indptr.cpu().numpy()
+            ix = self._graph.indices.cpu().numpy()
+            self._lazy["Lc"] = sparse.bsr_matrix((Lcb, ix, ip), shape=(self.n * d, self.n * d))
+        return self._lazy["Lc"]
+
+    @Lc.setter
+    def Lc(self, value):
+        self._lazy["Lc"] = value
+
+    # ------------------------------------------------------------------------------------------------------
+    def random_vector_field(self, seed=0):
+        """Generate random vector field over manifold (dataclass.py:91-103).  The uniform draw stays on the
+        host: NumPy's legacy global MT19937 stream is part of the reference's observable behaviour."""
+        np.random.seed(seed)
+        n, D = self.n, self._Xd.shape[1]
+        vectors = np.random.uniform(low=-0.5, high=0.5, size=(n, D))
+        vd = geo.to_device_f64(vectors, self.device)
+        g = self.device_array("gauges")
+        vd = geo.frame_apply_device(g, geo.frame_apply_device(g, vd, 0), 1).contiguous()
+        h = geo.get_handle(self.device.index)
+        h.call("rvgp_renorm_rows_f64", geo.I64(n), int(D), vd, None, None)
+        self.vectors = vd
+
+    def smooth_vector_field(self, t=100):
+        """Smooth vector field over manifold (dataclass.py:105-120): heat diffusion with Lc for the direction
+        and with L for the magnitude (smoothing.py:37-64)."""
+        if "vectors" in self._duals:
+            n, D, d = self.n, self._Xd.shape[1], self.dim_man
+            order, inv = self._perm
+            v = self.device_array("vectors")
+            vp = geo.gather_rows_device(v.reshape(n, D).contiguous(), order)
+            xl = geo.frame_apply_device(self._gauges_p, vp, 0)
+            st = {}
+            out = vector_diffusion_device(xl, float(t), self._A_Lc_p, self._A_L_p,
+                                          eig_Lc=(self._evals_Lc_d, self._U_Lc_p),
+                                          eig_L=(self._evals_L_d, self._U_L_p), hi=self._hi, stats=st)
+            self.stats["smoothing"] = st
+            outp = geo.frame_apply_device(self._gauges_p, out, 1)
+            self.vectors = geo.gather_rows_device(outp.contiguous(), inv)
+        else:
+            print('No vectors found. Nothing to smooth.')

@@ -214,7 +214,7 @@ def smallest_eigenpairs(A, k, upper_bound, lower_bound=0.0, tol=1e-12, nex=None,
     st["residual_max"] = float(res[:k].max())
     st["converged"] = bool((res[:k] <= tol_abs).all())
     evals = theta_d[:k].clone()
-    evecs = V[:, :k]
+    evecs = V[:, :k].contiguous()     # copy out so the (N x m) work buffers can be freed
     return evals, evecs
 
 

@@ -1,0 +1,349 @@
+"""Host-side mirror of the reference's ``RVGP/geometry.py`` over librvgp_b200.so.
+
+Public names, argument meaning and error behaviour follow the reference:
+``manifold_graph`` (geometry.py:100-123), ``compute_laplacian`` (:55-63),
+``compute_connection_laplacian`` (:14-52), ``compute_spectrum`` (:66-80), ``manifold_dimension`` (:83-97),
+``furthest_point_sampling`` (:126-162), ``project_to_manifold`` (:165-168), ``express_in_local_frame``
+(:171-176).  Every numerical stage runs in hand-written sm_100a kernels through the C ABI; there is no CPU
+path.  The ``*_device`` functions are the building blocks the data object uses (device tensors in / out).
+"""
+import math
+
+import numpy as np
+import torch
+
+from ._cabi import get_handle, I64, RvgpError, RVGP_ERR_RANK_DEFICIENT
+from .eigensolver import BsrMatrix, smallest_eigenpairs
+
+
+def _dev(device=None):
+    if not torch.cuda.is_available():
+        raise RuntimeError("rvgp_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device(device)
+
+
+def to_device_f64(x, device=None):
+    """numpy / torch / DLPack producer -> contiguous float64 CUDA tensor."""
+    dev = _dev(device)
+    if isinstance(x, torch.Tensor):
+        return x.to(device=dev, dtype=torch.float64).contiguous()
+    if hasattr(x, "__dlpack__") and not isinstance(x, np.ndarray):
+        return torch.from_dlpack(x).to(device=dev, dtype=torch.float64).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float64))).to(dev)
+
+
+class _Tensor(np.ndarray):
+    """ndarray with the ``.numpy()`` the reference calls on compute_spectrum's TF outputs (dataclass.py:50)."""
+
+    def numpy(self):
+        return np.asarray(self)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# device building blocks
+# ---------------------------------------------------------------------------------------------------------
+def knn_device(Xd, n_neighbors, q_begin=0, q_count=None, return_d2=False):
+    """K2.  (n, D) cuda f64 -> (q_count, nb) int32 neighbour ids, ascending (distance, index)."""
+    h = get_handle(Xd.device.index)
+    n, D = Xd.shape
+    if q_count is None:
+        q_count = n - q_begin
+    if n_neighbors >= n:
+        raise ValueError("Expected n_neighbors < n_samples_fit, but n_neighbors = %d, n_samples_fit = %d"
+                         % (n_neighbors, n))
+    idx = torch.empty((q_count, n_neighbors), dtype=torch.int32, device=Xd.device)
+    d2 = torch.empty((q_count, n_neighbors), dtype=torch.float64, device=Xd.device) if return_d2 else None
+    h.call("rvgp_knn_f64", Xd, int(n), int(D), int(q_begin), int(q_count), int(n_neighbors), idx, d2)
+    return (idx, d2) if return_d2 else idx
+
+
+def knn_to_csr_device(knn):
+    """K3.  Directed kNN lists -> symmetric CSR with self loops (union), int32, sorted columns."""
+    h = get_handle(knn.device.index)
+    n, k = knn.shape
+    wsb = h.query("rvgp_knn_to_csr_workspace_bytes", int(n), int(k))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=knn.device)
+    indptr = torch.empty(n + 1, dtype=torch.int32, device=knn.device)
+    indices = torch.empty(2 * n * k + n, dtype=torch.int32, device=knn.device)
+    nnz = torch.zeros(1, dtype=torch.int32, device=knn.device)
+    h.call("rvgp_knn_to_csr", knn, int(n), int(k), indptr, indices, nnz, ws, I64(wsb))
+    nnz = int(nnz.item())
+    return indptr, indices[:nnz].clone()
+
+
+def geodesic_neighbourhoods_device(indptr, indices, K, maxrow=None):
+    """K4.  Returns seq (n, K+1) int32 in the reference heap's pop order, counts (n)."""
+    h = get_handle(indptr.device.index)
+    n = indptr.numel() - 1
+    K = int(K)
+    if K >= n:
+        raise ValueError("Geodesic neighborhood size must be less than the total number of samples")
+    if maxrow is None:
+        maxrow = int((indptr[1:] - indptr[:-1]).max().item())
+    wsb = h.query("rvgp_geodesic_workspace_bytes", h._h, int(n), K, int(maxrow))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=indptr.device)
+    seq = torch.zeros((n, K + 1), dtype=torch.int32, device=indptr.device)
+    counts = torch.empty(n, dtype=torch.int32, device=indptr.device)
+    flags = torch.zeros(1, dtype=torch.int32, device=indptr.device)
+    h.call("rvgp_geodesic_neighbourhoods", indptr, indices, int(n), K, int(maxrow), seq, counts, flags, ws, I64(wsb))
+    f = int(flags.item())
+    if f & 2:
+        raise RvgpError(-1, "geodesic: decrease_val would fire (non-unit weights are not supported)")
+    if f & 4:
+        raise RvgpError(-6, "geodesic: node pool overflow")
+    return seq, counts
+
+
+def tangent_frames_device(Xd, seq, d):
+    """K5.  tangents (n, D, d) (first d left singular vectors), Sigma (n, d).  Raises RuntimeError like
+    ptu_dijkstra.pyx:119-123 when a neighbourhood does not span d dimensions."""
+    h = get_handle(Xd.device.index)
+    n, D = Xd.shape
+    Kp1 = seq.shape[1]
+    T = torch.empty((n, D, D), dtype=torch.float64, device=Xd.device)
+    S = torch.empty((n, D), dtype=torch.float64, device=Xd.device)
+    flag = torch.zeros(1, dtype=torch.int32, device=Xd.device)
+    h.call("rvgp_tangent_frames", Xd, int(n), int(D), seq, int(Kp1), int(d), T, S, flag)
+    if int(flag.item()) & 1:
+        raise RuntimeError("Local tangent space approximation failed, at least one geodesic "
+                           "neighborhood does not span d-dimensional space")
+    if d < D:
+        return slice_frames_device(T, d), S[:, :d].contiguous()
+    return T, S
+
+
+def slice_frames_device(T, d):
+    h = get_handle(T.device.index)
+    n, D, dfull = T.shape
+    if d == dfull:
+        return T
+    G = torch.empty((n, D, d), dtype=torch.float64, device=T.device)
+    h.call("rvgp_slice_frames", T, I64(n), int(D), int(dfull), int(d), G)
+    return G
+
+
+def explained_variance_device(Sigma):
+    """K6.  mean - std (population) over nodes of the cumulative explained variance (geometry.py:89-92)."""
+    h = get_handle(Sigma.device.index)
+    n, D = Sigma.shape
+    cum = torch.empty_like(Sigma)
+    h.call("rvgp_sigma_cumvar", Sigma, int(n), int(D), cum)
+    ws = torch.empty(max(1, h.query("rvgp_coldot_workspace_bytes", I64(n), int(D)) // 8), dtype=torch.float64,
+                     device=Sigma.device)
+    s = torch.empty(D, dtype=torch.float64, device=Sigma.device)
+    h.call("rvgp_coldot_f64", I64(n), int(D), cum, I64(D), None, I64(0), s, ws)
+    mean = s / n
+    h.call("rvgp_resid_sq_f64", I64(n), int(D), cum, I64(D), None, I64(0), mean, s, ws)
+    var_exp = mean.cpu().numpy() - np.sqrt(s.cpu().numpy() / n)
+    return var_exp
+
+
+def connections_device(gauges, indptr, indices, want_R=False):
+    """K7+K8.  Returns Lc block values (nnzb, d, d) [and the raw R blocks]."""
+    h = get_handle(gauges.device.index)
+    n, D, d = gauges.shape
+    nnzb = indices.numel()
+    Lc = torch.empty((nnzb, d, d), dtype=torch.float64, device=gauges.device)
+    R = torch.empty((nnzb, d, d), dtype=torch.float64, device=gauges.device) if want_R else None
+    h.call("rvgp_connections", gauges, int(n), int(D), int(d), indptr, indices, I64(nnzb), Lc, R)
+    return (Lc, R) if want_R else Lc
+
+
+def morton_order_device(Xd):
+    h = get_handle(Xd.device.index)
+    n, D = Xd.shape
+    wsb = h.query("rvgp_morton_order_workspace_bytes", int(n))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=Xd.device)
+    order = torch.empty(n, dtype=torch.int32, device=Xd.device)
+    inv = torch.empty(n, dtype=torch.int32, device=Xd.device)
+    h.call("rvgp_morton_order", Xd, int(n), int(D), order, inv, ws, I64(wsb))
+    return order, inv
+
+
+def csr_permute_device(indptr, indices, order, inv):
+    h = get_handle(indptr.device.index)
+    n = indptr.numel() - 1
+    wsb = h.query("rvgp_csr_permute_workspace_bytes", int(n))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=indptr.device)
+    ip = torch.empty_like(indptr)
+    ix = torch.empty_like(indices)
+    h.call("rvgp_csr_permute", int(n), indptr, indices, order, inv, ip, ix, ws, I64(wsb))
+    return ip, ix
+
+
+def gather_rows_device(A2d, perm, block=1):
+    """out[r] = A[perm[r // block] * block + r % block]."""
+    h = get_handle(A2d.device.index)
+    nrows, ncols = A2d.shape
+    out = torch.empty_like(A2d)
+    h.call("rvgp_gather_rows_f64", I64(nrows), int(ncols), A2d, I64(A2d.stride(0)), perm, int(block), out,
+           I64(out.stride(0)))
+    return out
+
+
+def frame_apply_device(gauges, x, mode, scale=1.0):
+    """mode 0: G^T x  (n,D,nc)->(n,d,nc);  mode 1: G x  (n,d,nc)->(n,D,nc)."""
+    h = get_handle(gauges.device.index)
+    n, D, d = gauges.shape
+    x3 = x.reshape(n, -1, 1) if x.dim() == 2 else x
+    nc = x3.shape[2]
+    out = torch.empty((n, d if mode == 0 else D, nc), dtype=torch.float64, device=gauges.device)
+    h.call("rvgp_frame_apply", gauges, I64(n), int(D), int(d), x3.contiguous(), out, int(nc), int(mode), float(scale))
+    return out.reshape(n, -1) if x.dim() == 2 else out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# public API (reference names)
+# ---------------------------------------------------------------------------------------------------------
+class ManifoldGraph:
+    """Device CSR of the symmetrised kNN graph with self loops.  ``to_networkx()`` materialises the
+    reference's networkx object (geometry.py:112,120-121) on demand."""
+
+    def __init__(self, indptr, indices, X=None, knn=None):
+        self.indptr, self.indices, self.X, self.knn = indptr, indices, X, knn
+        self.n = indptr.numel() - 1
+        self._nx = None
+
+    def __len__(self):
+        return self.n
+
+    def number_of_nodes(self):
+        return self.n
+
+    @property
+    def max_row(self):
+        return int((self.indptr[1:] - self.indptr[:-1]).max().item())
+
+    def scipy_adjacency(self):
+        from scipy import sparse
+        ip = self.indptr.cpu().numpy()
+        ix = self.indices.cpu().numpy()
+        return sparse.csr_matrix((np.ones(ix.size), ix, ip), shape=(self.n, self.n))
+
+    def to_networkx(self):
+        if self._nx is None:
+            import networkx as nx
+            G = nx.from_scipy_sparse_array(self.scipy_adjacency())
+            if self.X is not None:
+                Xh = self.X.cpu().numpy() if isinstance(self.X, torch.Tensor) else np.asarray(self.X)
+                nx.set_node_attributes(G, {i: Xh[i] for i in G.nodes}, "pos")
+            self._nx = G
+        return self._nx
+
+    @staticmethod
+    def from_any(G, device=None):
+        """Accept a ManifoldGraph or a networkx graph (the reference's inner-FFI argument type)."""
+        if isinstance(G, ManifoldGraph):
+            return G
+        import networkx as nx
+        from scipy import sparse
+        M = sparse.csr_matrix(nx.adjacency_matrix(G, weight="weight"))
+        M = M.maximum(M.T).tocsr()
+        M.sort_indices()
+        dev = _dev(device)
+        return ManifoldGraph(torch.from_numpy(M.indptr.astype(np.int32)).to(dev),
+                             torch.from_numpy(M.indices.astype(np.int32)).to(dev))
+
+
+def manifold_graph(X, typ="knn", n_neighbors=5, device=None):
+    """Fit graph over a pointset X (geometry.py:100-123).  Only typ='knn' is on the hot path."""
+    if typ != "knn":
+        raise NotImplementedError("typ='%s': only the kNN graph is on the B200 hot path (SURVEY.md 2.1)" % typ)
+    Xd = to_device_f64(X, device)
+    knn = knn_device(Xd, n_neighbors)
+    indptr, indices = knn_to_csr_device(knn)
+    return ManifoldGraph(indptr, indices, X=Xd, knn=knn)
+
+
+def manifold_dimension(Sigma, frac_explained=0.9):
+    """Estimate manifold dimension based on singular values (geometry.py:83-97)."""
+    Sd = to_device_f64(Sigma)
+    if frac_explained == 1.0:
+        return Sd.shape[1]
+    var_exp = explained_variance_device(Sd)
+    dim_man = np.where(var_exp >= frac_explained)[0][0] + 1
+    print("Fraction of variance explained: ", var_exp)
+    return int(dim_man)
+
+
+def _csr_host(G):
+    return G.indptr.cpu().numpy(), G.indices.cpu().numpy()
+
+
+def compute_laplacian(G, normalization=False):
+    """Graph Laplacian D - A as scipy CSR f64 (geometry.py:55-63).  Host materialisation of the device
+    pattern: diagonal = number of non-self neighbours, off-diagonal = -1."""
+    if normalization:
+        raise NotImplementedError("normalized Laplacian is not reached from the hot path (SURVEY.md 2.1)")
+    from scipy import sparse
+    G = ManifoldGraph.from_any(G)
+    ip, ix = _csr_host(G)
+    rows = np.repeat(np.arange(G.n), np.diff(ip))
+    deg = (np.diff(ip) - 1).astype(np.float64)
+    data = np.where(rows == ix, deg[rows], -1.0)
+    return sparse.csr_matrix((data, ix.copy(), ip.copy()), shape=(G.n, G.n))
+
+
+def compute_connection_laplacian(G, R, normalization=None):
+    """Connection Laplacian as scipy BSR (geometry.py:14-52): kron(L, 1_{dxd}) .* R."""
+    if normalization is not None:
+        raise NotImplementedError("normalization='rw' is not reached from the hot path (SURVEY.md 2.1)")
+    from scipy import sparse
+    G = ManifoldGraph.from_any(G)
+    n = G.n
+    dim = R.shape[0] // n
+    L = compute_laplacian(G)
+    Lc = sparse.kron(L, np.ones([dim, dim])).multiply(R)
+    return sparse.bsr_matrix(Lc, blocksize=(dim, dim))
+
+
+def compute_spectrum(laplacian, n_eigenpairs=None, dtype=None, tol=1e-12):
+    """Smallest-k eigenpairs (geometry.py:66-80): ascending eigenvalues, eigenvectors scaled by sqrt(#rows).
+    Accepts a scipy sparse matrix (CSR or BSR) and runs the GPU block eigensolver."""
+    from scipy import sparse
+    N = laplacian.shape[0]
+    if n_eigenpairs is None or n_eigenpairs >= N:
+        n_eigenpairs = N
+    dev = _dev()
+    if sparse.isspmatrix_bsr(laplacian) and laplacian.blocksize[0] == laplacian.blocksize[1]:
+        d = laplacian.blocksize[0]
+        B = laplacian
+    else:
+        d = 1
+        B = sparse.csr_matrix(laplacian)
+        B.sort_indices()
+    vals = torch.from_numpy(np.ascontiguousarray(B.data, dtype=np.float64).reshape(-1, d, d)).to(dev)
+    A = BsrMatrix(N // d, d, torch.from_numpy(B.indptr.astype(np.int32)).to(dev),
+                  torch.from_numpy(B.indices.astype(np.int32)).to(dev), vals)
+    # Gershgorin bound for symmetric matrices: max absolute row sum
+    hi = float(abs(sparse.csr_matrix(laplacian)).sum(1).max())
+    evals, evecs = smallest_eigenpairs(A, n_eigenpairs, upper_bound=hi, lower_bound=min(0.0, -1e-12 * hi), tol=tol)
+    evecs = evecs.cpu().numpy() * np.sqrt(N)
+    return evals.cpu().numpy().view(_Tensor), evecs.view(_Tensor)
+
+
+def project_to_manifold(x, gauges):
+    """Project vectors onto the local tangent frames (geometry.py:165-168)."""
+    Gd = to_device_f64(gauges)
+    coeffs = frame_apply_device(Gd, to_device_f64(x), 0)
+    return frame_apply_device(Gd, coeffs, 1).cpu().numpy()
+
+
+def express_in_local_frame(x, gauges, reverse=False):
+    """Express vectors in local coordinates (geometry.py:171-176)."""
+    Gd = to_device_f64(gauges)
+    return frame_apply_device(Gd, to_device_f64(x), 1 if reverse else 0).cpu().numpy()
+
+
+def furthest_point_sampling(x, N=None, spacing=0.1, start_idx=0, stop_crit=None):
+    """Greedy furthest-point sampling (geometry.py:126-162).  ``stop_crit`` is the README's stale alias of
+    ``spacing`` (README.md:70)."""
+    from .fps import furthest_point_sampling_device
+    if stop_crit is not None:
+        spacing = stop_crit
+    if spacing == 0.0:
+        return np.arange(len(x)), None
+    perm, lambdas = furthest_point_sampling_device(to_device_f64(x), N, spacing, start_idx)
+    return perm.cpu().numpy(), lambdas.cpu().numpy()

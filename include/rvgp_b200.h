@@ -155,6 +155,27 @@ int rvgp_axpy_f64(rvgp_handle_t h, int64_t nrows, int ncols, double a, const dou
 int rvgp_row_norms_f64(rvgp_handle_t h, int64_t n, int d, const double* x, double* out);
 int rvgp_renorm_rows_f64(rvgp_handle_t h, int64_t n, int d, double* x, const double* out_abs, const double* ind);
 
+/* C = alpha * op(A) op(B) + beta * C (layout flags as rvgp_dgemm_f64; no split-K, no K scaling) */
+int rvgp_dgemm_acc_f64(rvgp_handle_t h, int m, int n, int64_t k, double alpha, const double* A, int64_t lda,
+                       int a_kmajor, const double* B, int64_t ldb, int b_kmajor, double beta, double* C, int64_t ldc);
+
+/* ---- K13/K14: GP solve (replaces GPflow GPR's TF ops reached from main.py:55-58,77,80,111) -------------
+ * rvgp_potrf_f64: in-place lower Cholesky (blocked, right-looking) of an SPD row-major matrix; the strict upper
+ *   triangle is scratch.  flag (device int32): bit0 set when a pivot is not positive (-> RVGP_ERR_NOT_SPD at
+ *   the caller, like tf.linalg.cholesky failing).  workspace: rvgp_potrf_workspace_bytes(n); it keeps the
+ *   inverses of the diagonal blocks for rvgp_trsm_f64.
+ * rvgp_trsm_f64: solve L X = B (trans 0) or L^T X = B (trans 1) in place, B (n x nrhs) row-major;
+ *   scratch: 64*nrhs doubles.
+ * rvgp_kdiag_f64: K_diag[i] = sum_j S[j] X[i,j]^2 (kernels.py:63-67) without forming the N* x N* matrix. */
+int rvgp_potrf_f64(rvgp_handle_t h, double* A, int64_t lda, int n, int32_t* flag, void* workspace,
+                   int64_t workspace_bytes);
+int64_t rvgp_potrf_workspace_bytes(int n);
+int rvgp_trsm_f64(rvgp_handle_t h, const double* L, int64_t ldl, int n, double* B, int64_t ldb, int nrhs, int trans,
+                  const void* potrf_workspace, double* scratch);
+int rvgp_add_diag_f64(rvgp_handle_t h, double* A, int64_t lda, int n, double v);
+int rvgp_logdiag_sum_f64(rvgp_handle_t h, const double* A, int64_t lda, int n, double* out);
+int rvgp_kdiag_f64(rvgp_handle_t h, const double* X, int64_t ldx, int64_t n, int k, const double* S, double* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,7 +16,8 @@ template <bool A_KMAJOR, bool B_KMAJOR>
 __global__ void __launch_bounds__(256)
 dgemm_kernel(int M, int N, int64_t K, double alpha, const double* __restrict__ A, int64_t lda,
              const double* __restrict__ B, int64_t ldb, const double* __restrict__ scale_k,
-             double* __restrict__ C, int64_t ldc, int split_k, double* __restrict__ ws) {
+             double* __restrict__ C, int64_t ldc, int split_k, double* __restrict__ ws, double beta, int lower_only) {
+    if (lower_only && blockIdx.x * BN > blockIdx.y * BM + (BM - 1)) return;   // SYRK: tiles strictly above the diagonal
     __shared__ __align__(16) double As[BK][BM + PADM];
     __shared__ __align__(16) double Bs[BK][BN + PADM];
     const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
@@ -116,18 +117,23 @@ dgemm_kernel(int M, int N, int64_t K, double alpha, const double* __restrict__ A
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int gj = n0 + 2 * tx + 32 * (j >> 1) + (j & 1);
-            if (gj < N) out[(int64_t)gi * ldo + gj] = sc * acc[i][j];
+            if (gj < N) {
+                double v = sc * acc[i][j];
+                if (beta != 0.0 && split_k == 1) v = fma(beta, out[(int64_t)gi * ldo + gj], v);
+                out[(int64_t)gi * ldo + gj] = v;
+            }
         }
     }
 }
 
 __global__ void splitk_reduce_kernel(int M, int N, int split_k, double alpha, const double* __restrict__ ws,
-                                     double* __restrict__ C, int64_t ldc) {
+                                     double* __restrict__ C, int64_t ldc, double beta) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)M * N) return;
     double s = 0.0;
     for (int z = 0; z < split_k; ++z) s += ws[(int64_t)z * M * N + idx];   // fixed order: deterministic
-    C[(idx / N) * ldc + (idx % N)] = alpha * s;
+    double* c = C + (idx / N) * ldc + (idx % N);
+    *c = (beta != 0.0) ? fma(beta, *c, alpha * s) : alpha * s;
 }
 
 // ---- column reductions ------------------------------------------------------------------------------
@@ -218,15 +224,15 @@ extern "C" int64_t rvgp_dgemm_workspace_bytes(int m, int n, int split_k) {
     return split_k > 1 ? (int64_t)split_k * m * n * (int64_t)sizeof(double) : 0;
 }
 
-extern "C" int rvgp_dgemm_f64(rvgp_handle_t hh, int m, int n, int64_t k, double alpha, const double* A, int64_t lda,
-                              int a_kmajor, const double* B, int64_t ldb, int b_kmajor, const double* scale_k,
-                              double* C, int64_t ldc, int split_k, double* workspace) {
-    Handle* h = H(hh);
+namespace rvgp {
+int dgemm_launch(Handle* h, int m, int n, int64_t k, double alpha, const double* A, int64_t lda, int a_kmajor,
+                 const double* B, int64_t ldb, int b_kmajor, const double* scale_k, double beta, double* C, int64_t ldc,
+                 int split_k, double* workspace, int lower_only) {
     RVGP_REQUIRE(h, m >= 0 && n >= 0 && k >= 0 && split_k >= 1, "dgemm: bad sizes");
     RVGP_REQUIRE(h, split_k == 1 || workspace != nullptr, "dgemm: split_k > 1 needs a workspace");
     if (m == 0 || n == 0) return RVGP_OK;
     dim3 grid(cdiv(n, BN), cdiv(m, BM), split_k);
-#define RVGP_GEMM(AK, BKM) dgemm_kernel<AK, BKM><<<grid, 256, 0, h->stream>>>(m, n, k, alpha, A, lda, B, ldb, scale_k, C, ldc, split_k, workspace)
+#define RVGP_GEMM(AK, BKM) dgemm_kernel<AK, BKM><<<grid, 256, 0, h->stream>>>(m, n, k, alpha, A, lda, B, ldb, scale_k, C, ldc, split_k, workspace, beta, lower_only)
     if (a_kmajor && b_kmajor) RVGP_GEMM(true, true);
     else if (a_kmajor && !b_kmajor) RVGP_GEMM(true, false);
     else if (!a_kmajor && b_kmajor) RVGP_GEMM(false, true);
@@ -235,10 +241,25 @@ extern "C" int rvgp_dgemm_f64(rvgp_handle_t hh, int m, int n, int64_t k, double 
     RVGP_LAUNCH_OK(h, "dgemm_kernel");
     if (split_k > 1) {
         const int64_t tot = (int64_t)m * n;
-        splitk_reduce_kernel<<<cdiv(tot, 256), 256, 0, h->stream>>>(m, n, split_k, alpha, workspace, C, ldc);
+        splitk_reduce_kernel<<<cdiv(tot, 256), 256, 0, h->stream>>>(m, n, split_k, alpha, workspace, C, ldc, beta);
         RVGP_LAUNCH_OK(h, "splitk_reduce_kernel");
     }
     return RVGP_OK;
+}
+}  // namespace rvgp
+
+extern "C" int rvgp_dgemm_f64(rvgp_handle_t hh, int m, int n, int64_t k, double alpha, const double* A, int64_t lda,
+                              int a_kmajor, const double* B, int64_t ldb, int b_kmajor, const double* scale_k,
+                              double* C, int64_t ldc, int split_k, double* workspace) {
+    return dgemm_launch(H(hh), m, n, k, alpha, A, lda, a_kmajor, B, ldb, b_kmajor, scale_k, 0.0, C, ldc, split_k,
+                        workspace, 0);
+}
+
+// C = alpha * op(A) op(B) + beta * C   (same layout flags as rvgp_dgemm_f64; no split-K)
+extern "C" int rvgp_dgemm_acc_f64(rvgp_handle_t hh, int m, int n, int64_t k, double alpha, const double* A, int64_t lda,
+                                  int a_kmajor, const double* B, int64_t ldb, int b_kmajor, double beta, double* C,
+                                  int64_t ldc) {
+    return dgemm_launch(H(hh), m, n, k, alpha, A, lda, a_kmajor, B, ldb, b_kmajor, nullptr, beta, C, ldc, 1, nullptr, 0);
 }
 
 extern "C" int64_t rvgp_coldot_workspace_bytes(int64_t nrows, int ncols) {

@@ -1,0 +1,202 @@
+// K14: blocked right-looking Cholesky + triangular solves (FP64), K13 helper K_diag, small GP utilities.
+//
+// Replaces what GPflow/TensorFlow do for the reference's GPR (RVGP/main.py:55-58,77,80,111): tf.linalg.cholesky
+// of K + sigma^2 I, tf.linalg.triangular_solve, sum(log(diag L)); and ManifoldKernel.K_diag (RVGP/kernels.py:63-67)
+// WITHOUT forming the full N* x N* matrix the reference builds just to read its diagonal.
+//
+// potrf: for each 64-wide panel: (1) one CTA factors the diagonal block in shared memory and also emits its
+// inverse, (2) the panel below is multiplied by that inverse (dgemm), (3) the trailing lower triangle gets the
+// SYRK update as a tile-skipping dgemm.  FP64-FMA-pipe bound: M^3/3 flop.
+#include "common.cuh"
+
+namespace rvgp {
+
+int dgemm_launch(Handle* h, int m, int n, int64_t k, double alpha, const double* A, int64_t lda, int a_kmajor,
+                 const double* B, int64_t ldb, int b_kmajor, const double* scale_k, double beta, double* C, int64_t ldc,
+                 int split_k, double* workspace, int lower_only);
+
+constexpr int NB = 64;
+
+// Factor the nb x nb diagonal block at A (lower, in place; the strict upper part is left untouched) and write
+// inv(L_block) (lower, row-major nb x NB, zero above the diagonal) to Linv.  flag |= 1 on a non-positive pivot.
+__global__ void __launch_bounds__(256)
+potf2_inv_kernel(double* __restrict__ A, int64_t lda, int nb, double* __restrict__ Linv, int* __restrict__ flag) {
+    extern __shared__ double potf2_smem[];
+    double (*Ls)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(potf2_smem);
+    double (*Xs)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(potf2_smem + NB * (NB + 1));
+    const int t = threadIdx.x;
+    for (int e = t; e < NB * NB; e += 256) {
+        const int i = e / NB, j = e % NB;
+        Ls[i][j] = (i < nb && j <= i) ? A[(int64_t)i * lda + j] : ((i == j) ? 1.0 : 0.0);
+        Xs[i][j] = 0.0;
+    }
+    __syncthreads();
+    for (int j = 0; j < nb; ++j) {
+        if (t == 0) {
+            double p = Ls[j][j];
+            if (!(p > 0.0)) { atomicOr(flag, 1); p = 1.0; }
+            Ls[j][j] = sqrt(p);
+        }
+        __syncthreads();
+        const double djj = Ls[j][j];
+        for (int i = j + 1 + t; i < nb; i += 256) Ls[i][j] /= djj;
+        __syncthreads();
+        const int rem = nb - j - 1;
+        for (int e = t; e < rem * rem; e += 256) {
+            const int i = j + 1 + e / rem, k = j + 1 + e % rem;
+            if (k <= i) Ls[i][k] = fma(-Ls[i][j], Ls[k][j], Ls[i][k]);
+        }
+        __syncthreads();
+    }
+    // inverse by forward substitution, one column per thread
+    if (t < nb) {
+        const int c = t;
+        for (int i = c; i < nb; ++i) {
+            double s = (i == c) ? 1.0 : 0.0;
+            for (int k = c; k < i; ++k) s = fma(-Ls[i][k], Xs[k][c], s);
+            Xs[i][c] = s / Ls[i][i];
+        }
+    }
+    __syncthreads();
+    for (int e = t; e < nb * nb; e += 256) {
+        const int i = e / nb, j = e % nb;
+        if (j <= i) A[(int64_t)i * lda + j] = Ls[i][j];
+        Linv[i * NB + j] = Xs[i][j];
+    }
+}
+
+__global__ void add_diag_kernel(double* __restrict__ A, int64_t lda, int n, double v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) A[(int64_t)i * lda + i] += v;
+}
+
+// out[0] = sum_i log(A[i,i])   (single CTA, fixed order)
+__global__ void __launch_bounds__(256) logdiag_sum_kernel(const double* __restrict__ A, int64_t lda, int n, double* __restrict__ out) {
+    __shared__ double sm[256];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) s += log(A[(int64_t)i * lda + i]);
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = sm[0];
+}
+
+// kernels.py:63-67  K_diag[i] = sum_j S[j] X[i,j]^2
+__global__ void kdiag_kernel(const double* __restrict__ X, int64_t ldx, int64_t n, int k, const double* __restrict__ S,
+                             double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= n) return;
+    double s = 0.0;
+    for (int j = lane; j < k; j += 32) { const double v = __ldg(X + row * ldx + j); s = fma(__ldg(S + j) * v, v, s); }
+    s = warp_sum(s);
+    if (lane == 0) out[row] = s;
+}
+
+}  // namespace rvgp
+
+using namespace rvgp;
+
+extern "C" int64_t rvgp_potrf_workspace_bytes(int n) {
+    const int64_t nblk = (n + NB - 1) / NB;
+    return (int64_t)n * NB * 8 + nblk * NB * NB * 8;   // panel temp + inverses of the diagonal blocks
+}
+
+// In-place lower Cholesky of the symmetric positive definite A (n x n, row-major, only the lower triangle is
+// read or written).  workspace: rvgp_potrf_workspace_bytes(n); on return its tail holds inv(L_jj) of every
+// diagonal block (used by rvgp_trsm_f64).  flag (device int32, zeroed here): bit0 = not positive definite.
+extern "C" int rvgp_potrf_f64(rvgp_handle_t hh, double* A, int64_t lda, int n, int32_t* flag, void* workspace,
+                              int64_t workspace_bytes) {
+    Handle* h = H(hh);
+    RVGP_REQUIRE(h, n >= 0 && lda >= n, "potrf: bad sizes");
+    if (rvgp_potrf_workspace_bytes(n) > workspace_bytes) return set_error(h, RVGP_ERR_CAPACITY, "potrf: workspace too small%s%s");
+    double* T = (double*)workspace;
+    double* dinv = T + (int64_t)n * NB;
+    RVGP_CUDA_OK(h, cudaMemsetAsync(flag, 0, sizeof(int), h->stream));
+    const int potf2_smem_bytes = 2 * NB * (NB + 1) * (int)sizeof(double);
+    RVGP_CUDA_OK(h, cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, potf2_smem_bytes));
+    for (int j0 = 0, b = 0; j0 < n; j0 += NB, ++b) {
+        const int nb = (n - j0 < NB) ? n - j0 : NB;
+        double* Ajj = A + (int64_t)j0 * lda + j0;
+        double* Linv = dinv + (int64_t)b * NB * NB;
+        potf2_inv_kernel<<<1, 256, potf2_smem_bytes, h->stream>>>(Ajj, lda, nb, Linv, flag);
+        RVGP_LAUNCH_OK(h, "potf2_inv_kernel");
+        const int m2 = n - j0 - nb;
+        if (m2 > 0) {
+            double* A21 = A + (int64_t)(j0 + nb) * lda + j0;
+            // T = A21 * inv(L11)^T
+            int rc = dgemm_launch(h, m2, nb, nb, 1.0, A21, lda, 1, Linv, NB, 1, nullptr, 0.0, T, NB, 1, nullptr, 0);
+            if (rc) return rc;
+            RVGP_CUDA_OK(h, cudaMemcpy2DAsync(A21, lda * sizeof(double), T, NB * sizeof(double), (size_t)nb * sizeof(double),
+                                              (size_t)m2, cudaMemcpyDeviceToDevice, h->stream));
+            // A22 -= T T^T (lower tiles only)
+            double* A22 = A + (int64_t)(j0 + nb) * lda + (j0 + nb);
+            rc = dgemm_launch(h, m2, m2, nb, -1.0, T, NB, 1, T, NB, 1, nullptr, 1.0, A22, lda, 1, nullptr, 1);
+            if (rc) return rc;
+        }
+    }
+    return RVGP_OK;
+}
+
+// Solve L X = B (trans = 0) or L^T X = B (trans = 1) in place; L is the rvgp_potrf_f64 output (lower), B is
+// (n x nrhs) row-major.  `workspace` must be the SAME buffer rvgp_potrf_f64 used (diagonal-block inverses) and
+// additionally needs NB*nrhs doubles of scratch at `scratch`.
+extern "C" int rvgp_trsm_f64(rvgp_handle_t hh, const double* L, int64_t ldl, int n, double* B, int64_t ldb, int nrhs, int trans,
+                             const void* potrf_workspace, double* scratch) {
+    Handle* h = H(hh);
+    RVGP_REQUIRE(h, n >= 0 && nrhs >= 0 && (trans == 0 || trans == 1), "trsm: bad args");
+    if (n == 0 || nrhs == 0) return RVGP_OK;
+    const double* dinv = (const double*)potrf_workspace + (int64_t)n * NB;
+    const int nblk = (n + NB - 1) / NB;
+    for (int s = 0; s < nblk; ++s) {
+        const int b = trans ? nblk - 1 - s : s;
+        const int j0 = b * NB;
+        const int nb = (n - j0 < NB) ? n - j0 : NB;
+        const double* Linv = dinv + (int64_t)b * NB * NB;
+        double* Bj = B + (int64_t)j0 * ldb;
+        // X_j = inv(L_jj) B_j   or   inv(L_jj)^T B_j
+        int rc = dgemm_launch(h, nb, nrhs, nb, 1.0, Linv, NB, trans ? 0 : 1, Bj, ldb, 0, nullptr, 0.0, scratch, nrhs, 1, nullptr, 0);
+        if (rc) return rc;
+        RVGP_CUDA_OK(h, cudaMemcpy2DAsync(Bj, ldb * sizeof(double), scratch, (size_t)nrhs * sizeof(double),
+                                          (size_t)nrhs * sizeof(double), (size_t)nb, cudaMemcpyDeviceToDevice, h->stream));
+        if (!trans) {
+            const int m2 = n - j0 - nb;        // B[j+1:] -= L[j+1:, j] X_j
+            if (m2 > 0) {
+                rc = dgemm_launch(h, m2, nrhs, nb, -1.0, L + (int64_t)(j0 + nb) * ldl + j0, ldl, 1, Bj, ldb, 0, nullptr, 1.0,
+                                  B + (int64_t)(j0 + nb) * ldb, ldb, 1, nullptr, 0);
+                if (rc) return rc;
+            }
+        } else if (j0 > 0) {                   // B[:j] -= L[j, :j]^T X_j
+            rc = dgemm_launch(h, j0, nrhs, nb, -1.0, L + (int64_t)j0 * ldl, ldl, 0, Bj, ldb, 0, nullptr, 1.0, B, ldb, 1,
+                              nullptr, 0);
+            if (rc) return rc;
+        }
+    }
+    return RVGP_OK;
+}
+
+extern "C" int rvgp_add_diag_f64(rvgp_handle_t hh, double* A, int64_t lda, int n, double v) {
+    Handle* h = H(hh);
+    if (n == 0) return RVGP_OK;
+    add_diag_kernel<<<cdiv(n, 256), 256, 0, h->stream>>>(A, lda, n, v);
+    RVGP_LAUNCH_OK(h, "add_diag_kernel");
+    return RVGP_OK;
+}
+
+extern "C" int rvgp_logdiag_sum_f64(rvgp_handle_t hh, const double* A, int64_t lda, int n, double* out) {
+    Handle* h = H(hh);
+    logdiag_sum_kernel<<<1, 256, 0, h->stream>>>(A, lda, n, out);
+    RVGP_LAUNCH_OK(h, "logdiag_sum_kernel");
+    return RVGP_OK;
+}
+
+extern "C" int rvgp_kdiag_f64(rvgp_handle_t hh, const double* X, int64_t ldx, int64_t n, int k, const double* S, double* out) {
+    Handle* h = H(hh);
+    if (n == 0) return RVGP_OK;
+    kdiag_kernel<<<cdiv(n * 32, 256), 256, 0, h->stream>>>(X, ldx, n, k, S, out);
+    RVGP_LAUNCH_OK(h, "kdiag_kernel");
+    return RVGP_OK;
+}

@@ -1,0 +1,202 @@
+"""Mirror of the reference's ``RVGP/main.py``: ``train_gp`` (exported as ``RVGP.fit``), ``optimize_model_with_scipy``
+and ``manifold_GPR`` with ``transform`` / ``predict_f`` -- same names, argument meaning, prints and quirks
+(main.py:11-137), GPflow/TensorFlow replaced by rvgp_b200.gp.DeviceGPR.
+
+Reproduced on purpose (parity beats intent):
+  * ``noise_variance`` is accepted and DROPPED: the likelihood variance starts at GPflow's default 1.0 and is
+    trainable with lower bound 1e-6 (main.py:98-100).
+  * kernel parameters are created BEFORE ``set_default_positive_minimum(positivity_constraint)`` runs, so the
+    first fit of a process uses lower bound 0 and later fits 1e-2 (main.py:30 vs :52).
+  * the second output of ``transform`` is a VARIANCE (main.py:113-116).
+Accepted superset: ``transform`` also takes NumPy integer arrays, boolean masks and lists (the reference's type
+sniffing fails on them, App. B.1).
+"""
+import numpy as np
+import scipy.optimize
+import torch
+from sklearn.model_selection import train_test_split
+
+from . import params as P
+from .geometry import furthest_point_sampling, gather_rows_device, to_device_f64  # noqa: F401
+from .gp import DeviceGPR
+from .kernels import ManifoldKernel
+
+
+class _Gaussian:
+    """gpflow.likelihoods.Gaussian: variance Parameter, default 1.0, lower bound 1e-6."""
+
+    def __init__(self, variance=1.0, variance_lower_bound=1e-6):
+        self.variance = P.Parameter(variance, transform=P.positive(lower=variance_lower_bound), name='variance')
+
+
+def _node_rows_device(data, node_ind):
+    """evecs_Lc.reshape(n, D*k)[node_ind].reshape(-1, k) on the device (main.py:31,104-106)."""
+    Phi = data.device_array("evecs_Lc")
+    n = data.n
+    D = Phi.shape[0] // n
+    idx = torch.from_numpy(np.ascontiguousarray(node_ind, dtype=np.int32)).to(Phi.device)
+    out = torch.empty((len(node_ind) * D, Phi.shape[1]), dtype=torch.float64, device=Phi.device)
+    from ._cabi import get_handle, I64
+    h = get_handle(Phi.device.index)
+    h.call("rvgp_gather_rows_f64", I64(out.shape[0]), int(Phi.shape[1]), Phi, I64(Phi.stride(0)), idx, int(D), out,
+           I64(out.stride(0)))
+    return out
+
+
+def _as_node_indices(test_ind, n):
+    a = np.asarray(test_ind)
+    if a.dtype == bool:
+        return np.nonzero(a.reshape(-1))[0]
+    return a.reshape(-1).astype(np.int64)
+
+
+class manifold_GPR:
+    """GP regression model (replaces gpflow.models.GPR subclass, main.py:98-116)."""
+
+    def __init__(self, data, kernel, mean_function=None, noise_variance=None, likelihood=None, solver="auto"):
+        # like the reference, mean_function / noise_variance / likelihood are ignored (main.py:100)
+        X, Y = data
+        self.data = (to_device_f64(X), to_device_f64(Y))
+        self.kernel = kernel
+        self.likelihood = _Gaussian()
+        self._gpr = DeviceGPR(self.data[0], self.data[1], solver=solver)
+        self.solver = self._gpr.solver
+
+    @property
+    def trainable_parameters(self):
+        ps = list(self.kernel.trainable_parameters)
+        if self.likelihood.variance.trainable:
+            ps.append(self.likelihood.variance)
+        return ps
+
+    def log_marginal_likelihood(self):
+        S = self.kernel.eval_S(typ=self.kernel.typ)
+        return self._gpr.lml_and_grads(S, self.likelihood.variance.value, grads=False)
+
+    def training_loss(self):
+        return -self.log_marginal_likelihood()
+
+    def _loss_and_grad(self, u, plist):
+        for p, ui in zip(plist, u):
+            p.unconstrained = float(ui)
+        S, dS = self.kernel.eval_S(typ=self.kernel.typ, grads=True)
+        lml, gS, gnoise = self._gpr.lml_and_grads(S, self.likelihood.variance.value, grads=True)
+        g = []
+        for p in plist:
+            if p is self.likelihood.variance:
+                d = gnoise
+            else:
+                d = float(gS @ dS[p.name])
+            g.append(-d * p.transform.dforward(p.unconstrained))
+        return -lml, np.array(g)
+
+    def predict_f(self, Xnew, full_cov=False):
+        """(mean (N*,1), variance (N*,1)) as CUDA tensors with a ``.numpy()``-like host path via .cpu()."""
+        S = self.kernel.eval_S(typ=self.kernel.typ)
+        mean, var = self._gpr.predict(S, self.likelihood.variance.value, to_device_f64(Xnew))
+        return _HostView(mean), _HostView(var)
+
+    def transform(self, data, test_ind):
+        first = test_ind[0]
+        if isinstance(first, (float, np.floating)) or (hasattr(first, "__len__") and np.asarray(test_ind).dtype.kind == "f"):
+            test_x = to_device_f64(np.asarray(test_ind))                 # positional encodings given directly (main.py:108-109)
+            n_out = test_x.shape[0]
+        else:
+            nodes = _as_node_indices(test_ind, data.n)
+            test_x = _node_rows_device(data, nodes)
+            n_out = len(nodes)
+        f_pred_mean, f_pred_std = self.predict_f(test_x)
+        f_pred_mean = f_pred_mean.numpy().reshape(n_out, -1)
+        f_pred_std = f_pred_std.numpy().reshape(n_out, -1)
+        return f_pred_mean, f_pred_std
+
+
+class _HostView:
+    """Wraps a CUDA tensor; ``.numpy()`` copies to the host (what the reference calls on GPflow's outputs)."""
+
+    def __init__(self, t):
+        self.tensor = t
+
+    def numpy(self):
+        return self.tensor.cpu().numpy()
+
+    def __dlpack__(self, *a, **k):
+        return self.tensor.__dlpack__(*a, **k)
+
+    def __dlpack_device__(self):
+        return self.tensor.__dlpack_device__()
+
+
+def optimize_model_with_scipy(model, epochs):
+    """gpflow.optimizers.Scipy().minimize(training_loss, trainable_variables, method="l-bfgs-b",
+    options={"disp": True, "maxiter": epochs})  (main.py:87-95).  4 scalars on the host; every evaluation's
+    linear algebra on the device."""
+    plist = model.trainable_parameters
+    if not plist:
+        return model
+    u0 = np.array([p.unconstrained for p in plist])
+    res = scipy.optimize.minimize(lambda u: model._loss_and_grad(u, plist), u0, jac=True, method="L-BFGS-B",
+                                  options={"maxiter": epochs})
+    for p, ui in zip(plist, res.x):
+        p.unconstrained = float(ui)
+    model.opt_result = res
+    return model
+
+
+def train_gp(data,
+             train_ind=None,
+             n_inducing_points=None,
+             test_size=0.2,
+             kernel=None,
+             noise_variance=0.001,
+             kernel_lengthscale=None,
+             kernel_variance=None,
+             epochs=1000,
+             positivity_constraint=1e-2,
+             seed=0,
+             solver="auto"):
+
+    if train_ind is None:
+        train_ind = np.arange(data.n)
+    train_nodes = _as_node_indices(train_ind, data.n)
+
+    if kernel == 'rbf':
+        raise NotImplementedError("kernel='rbf' (channel-wise baseline on evecs_L) is a 'next' row (SURVEY.md 8f)")
+    if n_inducing_points is not None:
+        raise NotImplementedError("SGPR / inducing points is a 'next' row (SURVEY.md 8f)")
+
+    vec = data._duals["vectors"].get_dev(data.device) if hasattr(data, "_duals") else to_device_f64(data.vectors)
+    dim = vec.shape[1]
+    if kernel is None:
+        kernel = ManifoldKernel(data, nu=3 / 2, kappa=5, typ='matern', sigma_f=1.)
+
+    # split training and test set: sklearn on an index array gives the same rows as splitting the arrays
+    # (main.py:40-45); bit-exact host RNG, only indices go to the GPU
+    tr, te = train_test_split(np.arange(len(train_nodes)), test_size=test_size, random_state=seed)
+    in_train = _node_rows_device(data, train_nodes[tr])
+    in_test = _node_rows_device(data, train_nodes[te])
+    vd = vec.reshape(data.n, dim)
+    idx_tr = torch.from_numpy(train_nodes[tr]).to(vd.device)
+    idx_te = torch.from_numpy(train_nodes[te]).to(vd.device)
+    out_train = vd.index_select(0, idx_tr).reshape(-1, 1)
+    out_test = vd.index_select(0, idx_te).reshape(-1, 1)
+
+    P.set_default_positive_minimum(positivity_constraint)
+
+    GP = manifold_GPR((in_train, out_train), kernel, noise_variance=noise_variance, solver=solver)
+
+    if kernel_variance is not None:
+        kernel.variance.assign(kernel_variance)          # AttributeError for ManifoldKernel, as in the reference
+        P.set_trainable(kernel.variance, False)
+    if kernel_lengthscale is not None:
+        kernel.lengthscales.assign(kernel_lengthscale)
+        P.set_trainable(kernel.lengthscales, False)
+
+    GP = optimize_model_with_scipy(GP, epochs)
+
+    # test
+    out_pred, _ = GP.predict_f(in_test)
+    l2_error = np.linalg.norm(out_test.cpu().numpy() - out_pred.numpy(), axis=1).mean()
+    print("Relative l2 error is {}".format(l2_error))
+    GP.l2_error = float(l2_error)
+    return GP

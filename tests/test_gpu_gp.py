@@ -1,0 +1,141 @@
+"""GPU parity tests for the GP half (K13 Gram, K14 Cholesky/TRSM, K15 rank-k path, fit/transform) against the
+NumPy restatement of GPflow 2.6.5 (oracle/gp_oracle.py; parity unpinned -- GPflow is not installable here).
+Tolerances: LML 1e-10 rel, gradients 1e-7, predictive mean / variance 1e-6 rel (north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gp_oracle as GO
+from tests.conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    return torch.device("cuda", 0)
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(_dev())
+
+
+@pytest.mark.parametrize("n", [1, 5, 64, 65, 200, 777])
+def test_potrf_trsm(n):
+    from rvgp_b200.gp import _Chol
+    from rvgp_b200._cabi import get_handle
+    rng = np.random.default_rng(n)
+    A = rng.normal(size=(n, n + 3))
+    A = A @ A.T + 0.5 * np.eye(n)
+    Ad = _t(A)
+    ch = _Chol(get_handle(0), Ad, n)
+    ch.check()
+    L = np.tril(Ad.cpu().numpy())
+    Lref = np.linalg.cholesky(A)
+    np.testing.assert_allclose(L, Lref, rtol=1e-11, atol=1e-12)
+    B = rng.normal(size=(n, 7))
+    for trans in (0, 1):
+        Bd = _t(B)
+        ch.solve(Bd, trans)
+        ref = np.linalg.solve(Lref.T if trans else Lref, B)
+        np.testing.assert_allclose(Bd.cpu().numpy(), ref, rtol=1e-9, atol=1e-11)
+    assert abs(float(ch.logdiag_sum().item()) - np.log(np.diag(Lref)).sum()) < 1e-10 * max(1, n)
+
+
+def test_potrf_not_spd_raises():
+    from rvgp_b200.gp import _Chol
+    from rvgp_b200._cabi import get_handle, RvgpError
+    A = np.eye(100); A[70, 70] = -1.0
+    ch = _Chol(get_handle(0), _t(A), 100)
+    with pytest.raises(RvgpError):
+        ch.check()
+
+
+def test_kernel_class_K_and_Kdiag_dlpack():
+    from rvgp_b200.kernels import ManifoldKernel
+    g = load_golden("torus_n600_k20")
+
+    class D:
+        evals_Lc, evecs_Lc = g["evals_Lc"], g["evecs_Lc"]
+    for typ in ("matern", "se"):
+        kern = ManifoldKernel(D, nu=1.5, kappa=5.0, sigma_f=1.3, typ=typ)
+        S = GO.eval_S(g["evals_Lc"], 1.5, 5.0, 1.3, g["evecs_Lc"].shape[0], typ)
+        np.testing.assert_allclose(kern.eval_S(typ), S, rtol=1e-14)
+        X, X2 = g["evecs_Lc"][:301], g["evecs_Lc"][500:777]
+        Kd = kern.K(X, X2)                                     # numpy in
+        assert Kd.is_cuda and hasattr(Kd, "__dlpack__")
+        np.testing.assert_allclose(Kd.cpu().numpy(), GO.K(X, S, X2), rtol=1e-12, atol=1e-12)
+        Kd2 = kern.K(torch.utils.dlpack.from_dlpack(_t(X).__dlpack__()))      # CUDA DLPack in
+        np.testing.assert_allclose(Kd2.cpu().numpy(), GO.K(X, S), rtol=1e-12, atol=1e-12)
+        kd = kern.K_diag(_t(X))
+        np.testing.assert_allclose(kd.cpu().numpy(), GO.K_diag(X, S), rtol=1e-13)
+        np.testing.assert_allclose(kd.cpu().numpy(), np.diag(Kd2.cpu().numpy()), rtol=1e-12)
+
+
+@pytest.mark.parametrize("solver", ["dense", "lowrank"])
+def test_lml_gradients_and_predict_match_oracle(solver):
+    from rvgp_b200.gp import DeviceGPR
+    g = load_golden("sphere_n2000_k50")
+    n = 2000
+    np.random.seed(0)
+    train_ind = np.random.choice(np.arange(n), size=n // 2)
+    Xtr, Ytr, Xte, Yte = GO.prepare_training(g["evecs_Lc"], g["smoothed_field"], n, train_ind)
+    gp = DeviceGPR(_t(Xtr), _t(Ytr), solver=solver)
+    nv = g["evecs_Lc"].shape[0]
+    for (nu, kappa, sf, noise) in [(1.5, 5.0, 1.0, 1.0), (2.3, 3.1, 0.7, 0.05)]:
+        S = GO.eval_S(g["evals_Lc"], nu, kappa, sf, nv)
+        lml, dS, dn = gp.lml_and_grads(S, noise)
+        rl, rdS, rdn = GO.gpr_lml_dense(Xtr, Ytr, S, noise, grads=True)
+        assert abs(lml - rl) <= 1e-10 * abs(rl)
+        np.testing.assert_allclose(dS, rdS, rtol=1e-7, atol=1e-9 * np.abs(rdS).max())
+        assert abs(dn - rdn) <= 1e-7 * abs(rdn)
+        m, v = gp.predict(S, noise, _t(Xte))
+        rm, rv = GO.gpr_predict_dense(Xtr, Ytr, S, noise, Xte)
+        np.testing.assert_allclose(m.cpu().numpy(), rm, rtol=1e-6, atol=1e-8)
+        np.testing.assert_allclose(v.cpu().numpy(), rv[:, :1], rtol=1e-6, atol=1e-9)
+    if solver == "dense":
+        assert abs(gp.lml_and_grads(GO.eval_S(g["evals_Lc"], 1.5, 5.0, 1.0, nv), 1.0, grads=False) - (-2512.1283414532)) < 1e-6
+
+
+def test_readme_quickstart_end_to_end():
+    """README.md:83-107 on config C1 through the drop-in names; compared with the oracle running the same recipe."""
+    import RVGP
+    from RVGP.geometry import furthest_point_sampling
+    from rvgp_b200 import params as P
+    from tests.workloads import make_cloud
+    X = make_cloud("sphere", 2000, 0)
+    sample_ind, _ = furthest_point_sampling(X, stop_crit=0.0)
+    X = X[sample_ind]
+    g = load_golden("sphere_n2000_k50")
+    P.set_default_positive_minimum(0.0)                       # fresh-process state of gpflow.config
+    d = RVGP.create_data_object(X, n_eigenpairs=50)
+    d.random_vector_field(seed=1)
+    d.smooth_vector_field(t=100)
+    np.testing.assert_allclose(d.vectors, g["smoothed_field"], atol=1e-9)
+    np.random.seed(0)
+    train_ind = np.random.choice(np.arange(len(X)), size=int(0.5 * len(X)))
+    gp = RVGP.fit(d, train_ind=train_ind, noise_variance=0.001)
+    test_ind = [i for i in range(len(X)) if i not in train_ind]
+    mean, var = gp.transform(d, test_ind)
+    assert mean.shape == (len(test_ind), 3) and var.shape == (len(test_ind), 3)
+    # oracle: same data, same recipe, on the REFERENCE's eigenbasis (golden)
+    og = GO.train_gp(g["evecs_Lc"], g["evals_Lc"], g["smoothed_field"], 2000, train_ind, epochs=1000, kernel_lower=0.0,
+                     solver="lowrank")
+    om, ov = GO.transform(og, g["evecs_Lc"], 2000, test_ind)
+    p, q = gp.kernel, og.params()
+    assert abs(gp.opt_result.fun - og.opt_result.fun) < 1e-5 * abs(og.opt_result.fun)
+    np.testing.assert_allclose(mean, om, rtol=1e-4, atol=1e-5)          # after ~100s of L-BFGS-B steps
+    np.testing.assert_allclose(var, ov, rtol=1e-3, atol=1e-7)
+    err = np.linalg.norm(mean - d.vectors[test_ind], axis=1).mean()
+    assert err < 0.1
+    # at FIXED hyper-parameters (the oracle's optimum) predictions agree to 1e-6 (north_star tolerance)
+    gp.kernel.nu.assign(q["nu"]); gp.kernel.kappa.assign(q["kappa"]); gp.kernel.sigma_f.assign(q["sigma_f"])
+    gp.likelihood.variance.assign(q["noise"])
+    mean2, var2 = gp.transform(d, np.asarray(test_ind))                  # numpy int array accepted (App. B.1)
+    np.testing.assert_allclose(mean2, om, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(var2, ov, rtol=1e-6, atol=1e-9)
+    mask = np.zeros(len(X), dtype=bool); mask[test_ind] = True
+    mean3, _ = gp.transform(d, mask)                                     # boolean mask accepted
+    assert np.array_equal(mean3, mean2)
+    # second fit of the process: kernel lower bound is now 1e-2 (main.py:30 vs :52)
+    gp2 = RVGP.fit(d, train_ind=train_ind, epochs=5)
+    assert gp2.kernel.kappa.transform.lower == 1e-2 and gp.kernel.kappa.transform.lower == 0.0

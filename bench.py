@@ -1,0 +1,282 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the RVGP hot path on B200 (contract: see the task brief / DESIGN.md).
+
+One "step" = create_data_object + fit + transform on a synthetic point cloud (BASELINE.json metric:
+"create_data_object+fit+transform wall-s at 1M pts/k=500; Lanczos SpMM GB/s").
+  value    wall-seconds per step with inputs already resident in HBM (device tensors in, device tensors out)
+  e2e      the same step through the public drop-in API with HOST numpy buffers (H2D / D2H inside the timed region)
+  roofline the dominant kernel (fused block-SpMM of the Chebyshev filter): algorithmic bytes per launch / average
+           launch duration measured with CUDA events inside the timed steps
+  cpu_baseline / --impl reference: the reference's CPU algorithm (oracle port: sklearn kNN, the C heap-Dijkstra
+           restatement, NumPy SVDs, SciPy ARPACK eigsh, NumPy GP restatement) on a bounded sample of the workload.
+
+python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c4|c2|c1]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (cloud, n, k, description)
+    "c4": ("torus", 1_000_000, 500, "C4: 1M-point synthetic torus in R^3, k=500 eigenpairs, n_neighbors=10, fit on 50% (with replacement), transform on the rest"),
+    "c2": ("torus", 35_000, 200, "C2: 35k-point torus-like surface, k=200"),
+    "c1": ("sphere", 2_000, 50, "C1: README quick-start, 2k-point sphere, k=50"),
+}
+
+
+def make_inputs(wl):
+    from tests.workloads import make_cloud
+    kind, n, k, _ = WORKLOADS[wl]
+    X = make_cloud(kind, n, 0)
+    rng = np.random.RandomState(0)
+    train_ind = rng.choice(np.arange(n), size=n // 2)
+    mask = np.ones(n, dtype=bool)
+    mask[train_ind] = False
+    test_ind = np.nonzero(mask)[0]
+    # a smooth synthetic tangent-ish vector signal (the GP input `vectors`): gradient-like field of a harmonic
+    V = np.stack([np.cos(2 * X[:, 1]) + 0.3 * X[:, 2], np.sin(3 * X[:, 0]), 0.5 * np.cos(X[:, 0] + X[:, 1])], 1)
+    V /= np.linalg.norm(V, axis=1, keepdims=True)
+    return X, V, train_ind, test_ind, k
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def one_step(X, V, train_ind, test_ind, k, device_out):
+    import RVGP
+    d = RVGP.create_data_object(X, vectors=V, n_eigenpairs=k, verbose=False)
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        gp = RVGP.fit(d, train_ind=train_ind, noise_variance=0.001)
+    mean, var = gp.transform(d, test_ind, as_device=device_out)
+    return d, gp, mean, var
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    from rvgp_b200._cabi import get_handle
+    from rvgp_b200 import params as P
+    h = get_handle(local)
+    wl = args.workload
+    X, V, train_ind, test_ind, k = make_inputs(wl)
+    n, D = X.shape
+    Xd = torch.from_numpy(X).to(dev)
+    Vd = torch.from_numpy(V).to(dev)
+    Xp = torch.from_numpy(X).pin_memory()
+    Vp = torch.from_numpy(V).pin_memory()
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        outs = [fn() for _ in range(steps)]
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, outs
+
+    P.set_default_positive_minimum(0.0)
+    step_dev = lambda: one_step(Xd, Vd, train_ind, test_ind, k, True)
+    step_host = lambda: one_step(Xp.numpy(), Vp.numpy(), train_ind, test_ind, k, False)
+    for _ in range(args.warmup):
+        step_dev()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = h.launches
+    ms, outs = timed(step_dev, args.steps)
+    launches = (h.launches - l0) // max(1, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    # roofline of the dominant kernel from the stats of the timed steps
+    d_last = outs[-1][0]
+    st = d_last.stats["eig_Lc"]
+    A = d_last._A_Lc_p
+    t_launch = np.mean([o[0].stats["eig_Lc"]["t_filter"] / max(1, o[0].stats["eig_Lc"]["filter_launches"]) for o in outs])
+    panel = st["panel"]
+    bytes_fused = A.spmm_bytes(panel, fused=True)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = bytes_fused / t_launch / 1e9
+    share = np.mean([(o[0].stats["eig_Lc"]["t_filter"] + o[0].stats["eig_L"]["t_filter"]) for o in outs]) / (ms / 1e3 / args.steps)
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "spmm_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(wl)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "bsr_spmm_kernel (fused Chebyshev step, d=%d, %d columns)" % (A.d, panel),
+                "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "traffic": traffic, "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback",
+                "algorithmic_bytes_per_launch": int(bytes_fused), "avg_launch_ms": round(t_launch * 1e3, 4),
+                "bytes_per_launch_survey_formula": int(A.spmm_bytes(panel, fused=False)),
+                "share_of_step": round(float(share), 3)}
+    # e2e: host buffers in / out through the public API
+    del outs
+    ms_e2e, outs2 = timed(step_host, max(1, min(args.steps, 2)))
+    n_e2e = max(1, min(args.steps, 2))
+    mean = outs2[-1][2]
+    h2d = X.nbytes + V.nbytes + 4 * (len(train_ind) + len(test_ind)) * 2
+    d2h = 2 * mean.nbytes
+    res = {
+        "metric": "create_data_object+fit+transform wall-s", "value": round(ms / 1e3 / args.steps, 4), "unit": "s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 2),
+        "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOADS[wl][3], "n_points": n, "ambient_dim": D, "n_eigenpairs": k,
+                   "n_neighbors": 10, "parallelism": "replicas x%d" % world if world > 1 else "single GPU",
+                   "l2_policy": "inputs larger than L2 (block vectors %.1f GB, matrix %.2f GB)" %
+                                (A.nrows * st["m"] * 8 / 1e9, A.spmm_bytes(0) / 1e9)},
+        "e2e": {"value": round(ms_e2e / 1e3 / n_e2e, 4), "unit": "s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h)},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+        "stages_s": {a: round(b, 3) for a, b in d_last.timings.items()},
+        "eig_Lc": {a: (round(b, 3) if isinstance(b, float) else b) for a, b in st.items()},
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            res["cpu_baseline"] = cpu_baseline(wl)
+        print(json.dumps(res))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(wl, budget_n=None):
+    """The reference's CPU algorithm (oracle port) on a bounded sample of the workload: same generator and
+    parameters at reduced n and k so that it finishes in ~10-30 s, plus a linear-in-(n*k) extrapolation."""
+    from oracle import rvgp_oracle as O, gp_oracle as GO
+    from tests.workloads import make_cloud
+    kind, n_full, k_full, _ = WORKLOADS[wl]
+    n = budget_n or min(n_full, 12000)
+    k = min(k_full, 100)
+    X = make_cloud(kind, n, 0)
+    t0 = time.perf_counter()
+    d = O.create_data_object(X, n_eigenpairs=k)
+    t_create = time.perf_counter() - t0
+    V = np.stack([np.cos(2 * X[:, 1]) + 0.3 * X[:, 2], np.sin(3 * X[:, 0]), 0.5 * np.cos(X[:, 0] + X[:, 1])], 1)
+    V /= np.linalg.norm(V, axis=1, keepdims=True)
+    rng = np.random.RandomState(0)
+    train_ind = rng.choice(np.arange(n), size=n // 2)
+    mask = np.ones(n, dtype=bool); mask[train_ind] = False
+    t0 = time.perf_counter()
+    gp = GO.train_gp(d.evecs_Lc, d.evals_Lc, V, n, train_ind, epochs=1000, solver="lowrank")
+    GO.transform(gp, d.evecs_Lc, n, np.nonzero(mask)[0])
+    t_gp = time.perf_counter() - t0
+    total = t_create + t_gp
+    scale = (n_full * k_full) / float(n * k)
+    return {"value": round(total * scale, 1), "unit": "s", "cores": 1, "kind": "port",
+            "measured_s": round(total, 2),
+            "sample": "oracle port of the reference CPU path (sklearn kNN, C heap-Dijkstra, NumPy SVD, SciPy ARPACK eigsh, "
+                      "rank-k NumPy GP) on %s n=%d k=%d: %.1f s measured (create %.1f s, fit+transform %.1f s); value = measured x "
+                      "(n*k ratio %.0f) -- a LOWER bound, ARPACK's mat-vec count also grows with n and k" %
+                      (kind, n, k, total, t_create, t_gp, scale),
+            "stages_s": {a: round(b, 2) for a, b in d.timings.items()}}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = args.workload
+    vals = []
+    last = None
+    for i in range(args.warmup + args.steps):
+        last = cpu_baseline(wl, budget_n=8000)
+        if i >= args.warmup:
+            vals.append(last["value"])
+    v = float(np.mean(vals))
+    kind, n, k, desc = WORKLOADS[wl]
+    res = {"impl": "reference", "metric": "create_data_object+fit+transform wall-s", "value": round(v, 1), "unit": "s",
+           "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": round(v * 1e3, 1), "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic",
+           "config": {"workload": desc, "n_points": n, "n_eigenpairs": k},
+           "cpu_baseline": dict(last, value=round(v, 1)),
+           "e2e": {"value": round(v, 1), "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(res))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("RVGP_BENCH_WORKLOAD", "c4"), choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

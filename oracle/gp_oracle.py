@@ -193,7 +193,7 @@ class OracleGPR:
 
     def fit(self, epochs=1000, disp=False):
         res = scipy.optimize.minimize(self.loss_and_grad, self.u, jac=True, method="L-BFGS-B",
-                                      options={"disp": disp, "maxiter": epochs})
+                                      options={"maxiter": epochs})
         self.u = res.x
         self.opt_result = res
         return self

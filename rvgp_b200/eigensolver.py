@@ -100,7 +100,7 @@ class _Dense:
 
 
 def smallest_eigenpairs(A, k, upper_bound, lower_bound=0.0, tol=1e-12, nex=None, seed=0, max_outer=80,
-                        cond_max=1e7, deg0=20, panel=None, stats=None, verbose=False):
+                        cond_max=1e6, deg0=20, panel=None, stats=None, verbose=False):
     """Smallest k eigenpairs of the symmetric PSD BsrMatrix ``A``.
 
     upper_bound: a rigorous upper bound of the spectrum (2 * max degree for (connection) Laplacians).
@@ -122,7 +122,7 @@ def smallest_eigenpairs(A, k, upper_bound, lower_bound=0.0, tol=1e-12, nex=None,
     lo_spec = float(lower_bound)
     tol_abs = tol * hi
     st = stats if stats is not None else {}
-    st.update(dict(N=N, k=k, m=m, panel=panel, spmm_launches=0, filter_col_degrees=0, outer=0,
+    st.update(dict(N=N, k=k, m=m, panel=panel, spmm_launches=0, filter_launches=0, filter_col_degrees=0, outer=0,
                    t_filter=0.0, t_dense=0.0, t_host=0.0))
 
     B1 = torch.empty((N, m), dtype=torch.float64, device=dev)
@@ -157,30 +157,37 @@ def smallest_eigenpairs(A, k, upper_bound, lower_bound=0.0, tol=1e-12, nex=None,
             h.call("rvgp_cheb_filter_f64", A.nbrows, A.d, A.indptr, A.indices, A.vals, Vp, I64(V.stride(0)),
                    w0, w1, I64(panel), int(p1 - p0), dg, lo_spec, float(a_cut), hi)
             st["spmm_launches"] += dg
+            st["filter_launches"] += dg
             st["filter_col_degrees"] += dg * (p1 - p0)
         ev1.record()
         # ---- orthonormalise: column scaling + Cholesky-QR, then Rayleigh-Ritz with the second
         #      Cholesky folded into the projected problem ---------------------------------------------
-        nrm = dense.coldot(V, V)
-        inv = torch.rsqrt(nrm)
-        dense.colscale(V, inv)
-        dense.gram(V, V, Gd)
-        t0 = time.perf_counter()
-        G = Gd.cpu().numpy()
-        G = 0.5 * (G + G.T)
-        R = np.linalg.cholesky(G).T                       # G = R^T R
-        Rinv = _tri_inv_upper(R)
-        st["t_host"] += time.perf_counter() - t0
-        Cd.copy_(torch.from_numpy(np.ascontiguousarray(Rinv)))
-        dense.apply(V, Cd, W)                              # W = V R^-1   (nearly orthonormal)
-        V, W = W, V
+        # CholeskyQR passes until one succeeds WITHOUT a diagonal shift (shifted CholeskyQR3: a failed /
+        # shifted pass still reduces cond(V) by orders of magnitude, so the next pass is safe)
+        for _pass in range(4):
+            nrm = dense.coldot(V, V)
+            inv = torch.rsqrt(nrm)
+            dense.colscale(V, inv)
+            dense.gram(V, V, Gd)
+            G = Gd.cpu().numpy()
+            t0 = time.perf_counter()
+            G = 0.5 * (G + G.T)
+            R, shifted = _chol_upper_shifted(G)
+            Rinv = _tri_inv_upper(R)
+            st["t_host"] += time.perf_counter() - t0
+            Cd.copy_(torch.from_numpy(np.ascontiguousarray(Rinv)))
+            dense.apply(V, Cd, W)                          # W = V R^-1   (nearly orthonormal)
+            V, W = W, V
+            st["cholqr_passes"] = st.get("cholqr_passes", 0) + 1
+            if not shifted:
+                break
         A.matmat(V, out=W, h=h)                            # W = A V
         st["spmm_launches"] += math.ceil(m / 64)
         dense.gram(V, V, Gd)
         dense.gram(V, W, Hd)
-        t0 = time.perf_counter()
         G = Gd.cpu().numpy(); G = 0.5 * (G + G.T)
         Hm = Hd.cpu().numpy(); Hm = 0.5 * (Hm + Hm.T)
+        t0 = time.perf_counter()
         R2 = np.linalg.cholesky(G).T
         R2inv = _tri_inv_upper(R2)
         Hm = R2inv.T @ Hm @ R2inv
@@ -216,6 +223,24 @@ def smallest_eigenpairs(A, k, upper_bound, lower_bound=0.0, tol=1e-12, nex=None,
     evals = theta_d[:k].clone()
     evecs = V[:, :k].contiguous()     # copy out so the (N x m) work buffers can be freed
     return evals, evecs
+
+
+def _chol_upper_shifted(G):
+    """Upper Cholesky factor of the (unit-diagonal) Gram matrix; on breakdown retry with a growing diagonal
+    shift (Fukaya et al., shifted CholeskyQR).  Returns (R, shifted)."""
+    try:
+        return np.linalg.cholesky(G).T, False
+    except np.linalg.LinAlgError:
+        pass
+    m = G.shape[0]
+    shift = 1e-13 * m
+    while True:
+        try:
+            return np.linalg.cholesky(G + shift * np.eye(m)).T, True
+        except np.linalg.LinAlgError:
+            shift *= 100.0
+            if shift > 1.0:
+                raise
 
 
 def _tri_inv_upper(R):

@@ -41,6 +41,8 @@ int rvgp_sm_count(rvgp_handle_t h);
 /* kernels launched through this handle since creation (bench.py "gpu_launches") */
 unsigned long long rvgp_launch_count(rvgp_handle_t h);
 int rvgp_version(void);
+/* tuning knobs for experiments: "spmm_lpr" = lanes per block row in rvgp_bsr_spmm_f64 (0 auto | 8 | 16 | 32) */
+int rvgp_set_option(rvgp_handle_t h, const char* key, int value);
 
 /* ---- K9: block-CSR SpMM (replaces the ARPACK mat-vec inside geometry.py:73) ------------------------
  * Y = alpha * (A @ X) + beta * X + gamma * W      (the Chebyshev three-term step when beta,gamma != 0)
@@ -60,6 +62,24 @@ int rvgp_bsr_spmm_f64(rvgp_handle_t h, int nbrows, int d, const int32_t* indptr,
 int rvgp_cheb_filter_f64(rvgp_handle_t h, int nbrows, int d, const int32_t* indptr, const int32_t* indices,
                          const double* vals, double* V, int64_t ldv, double* work0, double* work1,
                          int64_t ldw, int ncols, int degree, double lo_spec, double lo_cut, double hi);
+
+/* ---- K9 v2: shared-memory-staged SpMM.  rvgp_bsr_tile_plan lists, for every tile of TR consecutive block rows,
+ * the unique neighbour nodes (ucols, padded to ucap per tile; tile_u = count) and rewrites each entry's column as
+ * a 16-bit index into that list (lidx).  info (device int32[3]): [0] max unique per tile, [1] != 0 plan invalid
+ * (keep using rvgp_bsr_spmm_f64), [2] max entries per tile.  rvgp_bsr_spmm_tiled_f64 has the contract of
+ * rvgp_bsr_spmm_f64 but stages X rows and block values through shared memory with cp.async.bulk; it needs even
+ * ncols, even ldx and 16-byte aligned X / vals.  rvgp_cheb_filter_tiled_f64 = rvgp_cheb_filter_f64 on top of it
+ * (work0..2: three CONTIGUOUS (nrows x ncols) scratch panels). */
+int rvgp_bsr_tile_plan(rvgp_handle_t h, int nbrows, const int32_t* indptr, const int32_t* indices, int TR, int ucap,
+                       int32_t* tile_u, int32_t* ucols, uint16_t* lidx, int32_t* info);
+int rvgp_bsr_spmm_tiled_f64(rvgp_handle_t h, int nbrows, int d, int TR, int ucap, int umax, int nemax,
+                            const int32_t* indptr, const int32_t* tile_u, const int32_t* ucols, const uint16_t* lidx,
+                            const double* vals, const double* X, int64_t ldx, const double* W, int64_t ldw, double* Y,
+                            int64_t ldy, int ncols, double alpha, double beta, double gamma);
+int rvgp_cheb_filter_tiled_f64(rvgp_handle_t h, int nbrows, int d, int TR, int ucap, int umax, int nemax,
+                               const int32_t* indptr, const int32_t* tile_u, const int32_t* ucols, const uint16_t* lidx,
+                               const double* vals, double* V, int64_t ldv, double* work0, double* work1, double* work2,
+                               int ncols, int degree, double lo_spec, double lo_cut, double hi);
 
 /* ---- K10: dense FP64 kernels for orthogonalisation / Rayleigh-Ritz ---------------------------------
  * C (m x n, ldc) = alpha * op(A) * op(B).  Layout flags say which index of each operand is contiguous:
@@ -86,9 +106,10 @@ int rvgp_resid_sq_f64(rvgp_handle_t h, int64_t nrows, int ncols, const double* W
 int64_t rvgp_coldot_workspace_bytes(int64_t nrows, int ncols);
 /* A[r,c] *= s[c] */
 int rvgp_colscale_f64(rvgp_handle_t h, int64_t nrows, int ncols, double* A, int64_t lda, const double* s);
-/* deterministic counter-based uniform(-1,1) fill: element (r,c) depends only on (seed, r, c0+c) */
+/* deterministic counter-based uniform(-1,1) fill: element (r,c) depends only on (seed, row_offset+r, col_offset+c),
+ * so a row-sharded block vector is the same global vector for any number of ranks */
 int rvgp_fill_uniform_f64(rvgp_handle_t h, int64_t nrows, int ncols, double* A, int64_t lda,
-                          uint64_t seed, int64_t col_offset);
+                          uint64_t seed, int64_t col_offset, int64_t row_offset);
 /* out[r, c] = in[perm[r], c] for r < nrows (row gather; used for the locality permutation) */
 int rvgp_gather_rows_f64(rvgp_handle_t h, int64_t nrows, int ncols, const double* in, int64_t ldin,
                          const int32_t* perm, int block, double* out, int64_t ldout);

@@ -181,6 +181,13 @@ class OracleGPR:
     def loss_and_grad(self, u):
         """training_loss = -LML and its gradient w.r.t. the unconstrained variables."""
         self.n_eval += 1
+        try:
+            with np.errstate(all="ignore"):
+                return self._loss_and_grad(u)
+        except (np.linalg.LinAlgError, ValueError, FloatingPointError):
+            return 1e50, np.zeros_like(u)     # non-finite / non-SPD trial point: make the line search back off
+
+    def _loss_and_grad(self, u):
         p = self.params(u)
         S, dnu, dka, dsf = eval_S(self.evals, p["nu"], p["kappa"], p["sigma_f"], self.nv, self.typ, grads=True)
         if self.solver == "lowrank":
@@ -189,6 +196,8 @@ class OracleGPR:
             lml, dS, dnoise = gpr_lml_dense(self.X, self.Y, S, p["noise"], grads=True)
         dtheta = dict(nu=dS @ dnu, kappa=dS @ dka, sigma_f=dS @ dsf, noise=dnoise)
         g = np.array([dtheta[n] * sigmoid(ui) for n, ui in zip(self.names, u)])
+        if not (np.isfinite(lml) and np.all(np.isfinite(g))):
+            raise FloatingPointError("non-finite LML")
         return -lml, -g
 
     def fit(self, epochs=1000, disp=False):

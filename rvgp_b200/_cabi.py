@@ -120,6 +120,11 @@ class Handle:
     def query(self, name, *args):
         return getattr(self.lib, name)(*[_conv(a) for a in args])
 
+    def set_option(self, key, value):
+        rc = self.lib.rvgp_set_option(self._h, ctypes.c_char_p(key.encode()), ctypes.c_int(int(value)))
+        if rc != 0:
+            raise ValueError(self.lib.rvgp_last_error(self._h).decode())
+
     @property
     def launches(self):
         return int(self.lib.rvgp_launch_count(self._h))

@@ -15,6 +15,8 @@ struct Handle {
     int sm_count;
     char last_error[512];
     unsigned long long launches;  // kernels launched through this handle (bench.py: gpu_launches)
+    int spmm_lpr;                 // tuning: lanes per block row in the gather SpMM (0 = auto)
+    int spmm_v1;                  // tuning: force the 64-bit-load kernel
 };
 
 inline Handle* H(rvgp_handle_t h) { return reinterpret_cast<Handle*>(h); }

@@ -14,6 +14,8 @@ extern "C" int rvgp_create(int device, rvgp_handle_t* out) {
     h->device = device;
     h->stream = nullptr;
     h->launches = 0;
+    h->spmm_lpr = 0;
+    h->spmm_v1 = 0;
     h->last_error[0] = 0;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete h; return RVGP_ERR_CUDA; }
@@ -36,3 +38,11 @@ extern "C" int rvgp_set_stream(rvgp_handle_t hh, void* s) {
 extern "C" const char* rvgp_last_error(rvgp_handle_t hh) { return hh ? H(hh)->last_error : "null handle"; }
 extern "C" int rvgp_sm_count(rvgp_handle_t hh) { return hh ? H(hh)->sm_count : 0; }
 extern "C" unsigned long long rvgp_launch_count(rvgp_handle_t hh) { return hh ? H(hh)->launches : 0ull; }
+
+// Tuning knobs (benchmarks / experiments).  "spmm_lpr": lanes per block row in rvgp_bsr_spmm_f64 (0 auto, 8, 16, 32).
+extern "C" int rvgp_set_option(rvgp_handle_t hh, const char* key, int value) {
+    if (!hh || !key) return RVGP_ERR_BAD_ARG;
+    if (strcmp(key, "spmm_lpr") == 0) { H(hh)->spmm_lpr = value; return RVGP_OK; }
+    if (strcmp(key, "spmm_v1") == 0) { H(hh)->spmm_v1 = value; return RVGP_OK; }
+    return set_error(H(hh), RVGP_ERR_BAD_ARG, "unknown option %s%s", key);
+}

@@ -197,12 +197,12 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
 }
 
 __global__ void fill_uniform_kernel(int64_t nrows, int ncols, double* __restrict__ A, int64_t lda, uint64_t seed,
-                                    int64_t col_offset) {
+                                    int64_t col_offset, int64_t row_offset) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nrows * ncols) return;
     const int64_t r = idx / ncols;
     const int64_t c = idx % ncols + col_offset;
-    const uint64_t hsh = splitmix64(splitmix64(seed ^ (uint64_t)r * 0x100000001B3ull) + (uint64_t)c);
+    const uint64_t hsh = splitmix64(splitmix64(seed ^ (uint64_t)(r + row_offset) * 0x100000001B3ull) + (uint64_t)c);
     A[r * lda + (c - col_offset)] = (double)(hsh >> 11) * (2.0 / 9007199254740992.0) - 1.0;
 }
 
@@ -300,11 +300,11 @@ extern "C" int rvgp_colscale_f64(rvgp_handle_t hh, int64_t nrows, int ncols, dou
 }
 
 extern "C" int rvgp_fill_uniform_f64(rvgp_handle_t hh, int64_t nrows, int ncols, double* A, int64_t lda, uint64_t seed,
-                                     int64_t col_offset) {
+                                     int64_t col_offset, int64_t row_offset) {
     Handle* h = H(hh);
     const int64_t tot = nrows * ncols;
     if (tot == 0) return RVGP_OK;
-    fill_uniform_kernel<<<cdiv(tot, 256), 256, 0, h->stream>>>(nrows, ncols, A, lda, seed, col_offset);
+    fill_uniform_kernel<<<cdiv(tot, 256), 256, 0, h->stream>>>(nrows, ncols, A, lda, seed, col_offset, row_offset);
     RVGP_LAUNCH_OK(h, "fill_uniform_kernel");
     return RVGP_OK;
 }

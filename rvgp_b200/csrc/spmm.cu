@@ -92,23 +92,168 @@ bsr_spmm_kernel(int nbrows, const int* __restrict__ indptr, const int* __restric
     }
 }
 
+// ---- v2: 128-bit loads ---------------------------------------------------------------------------------------
+// ncu (profiles/r01_spmm_*): the L1 data pipe moves 64 B per wavefront for 64-bit-per-lane loads, so the v1 kernel is
+// capped near 64 B/clk/SM.  Here every lane owns PAIRS of adjacent columns and gathers them with LDG.128 (double2),
+// and even-sized value blocks are read as double2 as well: twice the bytes per wavefront, half the load instructions.
+// Needs even ncols / leading dimensions and 16-byte aligned X, W, Y (the dispatcher falls back to v1 otherwise).
+template <int D, int LPR, int CPL2, int U, bool PATTERN>
+__global__ void __launch_bounds__(256)
+bsr_spmm_v2_kernel(int nbrows, const int* __restrict__ indptr, const int* __restrict__ indices,
+                   const double* __restrict__ vals, const double* __restrict__ X, int64_t ldx,
+                   const double* __restrict__ W, int64_t ldw, double* __restrict__ Y, int64_t ldy,
+                   int ncols, double alpha, double beta, double gamma, int rows_per_group) {
+    constexpr int GPW = 32 / LPR;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane / LPR, l = lane % LPR;
+    const int rows_per_cta = 8 * GPW * rows_per_group;
+    const int row0 = blockIdx.x * rows_per_cta;
+    const int npairs = ncols >> 1;
+    bool colok[CPL2];
+#pragma unroll
+    for (int cc = 0; cc < CPL2; ++cc) colok[cc] = (l + LPR * cc) < npairs;
+
+    for (int it = 0; it < rows_per_group; ++it) {
+        const int i = row0 + it * (8 * GPW) + warp * GPW + g;
+        if (i >= nbrows) continue;
+        const int e0 = __ldg(indptr + i), e1 = __ldg(indptr + i + 1);
+        double2 acc[D][CPL2];
+#pragma unroll
+        for (int p = 0; p < D; ++p)
+#pragma unroll
+            for (int cc = 0; cc < CPL2; ++cc) acc[p][cc] = make_double2(0.0, 0.0);
+
+        for (int e = e0; e < e1; e += U) {
+            int j[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) j[u] = (e + u < e1) ? __ldg(indices + e + u) : -1;
+            double2 x[U][D][CPL2];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int q = 0; q < D; ++q)
+#pragma unroll
+                    for (int cc = 0; cc < CPL2; ++cc)
+                        x[u][q][cc] = (j[u] >= 0 && colok[cc])
+                                          ? __ldg(reinterpret_cast<const double2*>(X + ((int64_t)j[u] * D + q) * ldx) + l + LPR * cc)
+                                          : make_double2(0.0, 0.0);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (j[u] < 0) continue;
+                if (PATTERN) {
+                    const double r = (j[u] == i) ? (double)(e1 - e0 - 1) : -1.0;
+#pragma unroll
+                    for (int cc = 0; cc < CPL2; ++cc) {
+                        acc[0][cc].x = fma(r, x[u][0][cc].x, acc[0][cc].x);
+                        acc[0][cc].y = fma(r, x[u][0][cc].y, acc[0][cc].y);
+                    }
+                } else {
+                    const double* rp = vals + (int64_t)(e + u) * (D * D);
+                    double r[D * D];
+                    if ((D * D) % 2 == 0) {
+#pragma unroll
+                        for (int v = 0; v < D * D; v += 2) {
+                            const double2 rv = __ldg(reinterpret_cast<const double2*>(rp + v));
+                            r[v] = rv.x; r[v + 1] = rv.y;
+                        }
+                    } else {
+#pragma unroll
+                        for (int v = 0; v < D * D; ++v) r[v] = __ldg(rp + v);
+                    }
+#pragma unroll
+                    for (int p = 0; p < D; ++p)
+#pragma unroll
+                        for (int q = 0; q < D; ++q)
+#pragma unroll
+                            for (int cc = 0; cc < CPL2; ++cc) {
+                                acc[p][cc].x = fma(r[p * D + q], x[u][q][cc].x, acc[p][cc].x);
+                                acc[p][cc].y = fma(r[p * D + q], x[u][q][cc].y, acc[p][cc].y);
+                            }
+                }
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < D; ++p)
+#pragma unroll
+            for (int cc = 0; cc < CPL2; ++cc) {
+                if (!colok[cc]) continue;
+                const int c2 = l + LPR * cc;
+                const int64_t r = (int64_t)i * D + p;
+                double2 y = make_double2(alpha * acc[p][cc].x, alpha * acc[p][cc].y);
+                if (beta != 0.0) {
+                    const double2 xv = __ldg(reinterpret_cast<const double2*>(X + r * ldx) + c2);
+                    y.x = fma(beta, xv.x, y.x); y.y = fma(beta, xv.y, y.y);
+                }
+                if (gamma != 0.0) {
+                    const double2 wv = __ldg(reinterpret_cast<const double2*>(W + r * ldw) + c2);
+                    y.x = fma(gamma, wv.x, y.x); y.y = fma(gamma, wv.y, y.y);
+                }
+                reinterpret_cast<double2*>(Y + r * ldy)[c2] = y;
+            }
+    }
+}
+
+template <int D, bool PATTERN>
+static int launch_spmm_v2(Handle* h, int nbrows, const int* indptr, const int* indices, const double* vals,
+                          const double* X, int64_t ldx, const double* W, int64_t ldw, double* Y, int64_t ldy,
+                          int ncols, double alpha, double beta, double gamma) {
+    const int rpg = 8;
+    const int npairs = ncols >> 1;
+#define RVGP_V2(LPR, CPL2)                                                                                 \
+    do {                                                                                                   \
+        constexpr int U = (D * CPL2 <= 2) ? 4 : ((D * CPL2 <= 4) ? 2 : 1);                                 \
+        const int rows_per_cta = 8 * (32 / LPR) * rpg;                                                     \
+        bsr_spmm_v2_kernel<D, LPR, CPL2, U, PATTERN><<<cdiv(nbrows, rows_per_cta), 256, 0, h->stream>>>(   \
+            nbrows, indptr, indices, vals, X, ldx, W, ldw, Y, ldy, ncols, alpha, beta, gamma, rpg);        \
+    } while (0)
+    int lpr = h->spmm_lpr;
+    if (lpr != 8 && lpr != 16 && lpr != 32) {
+        // measured on B200 (tools/profile_spmm2.py): best when every lane carries about two double2 row-fragments
+        // per stored block, i.e. D * CPL2 ~ 2
+        const int want = npairs * D / 2;
+        lpr = (want <= 8) ? 8 : (want <= 16 ? 16 : 32);
+    }
+    while (lpr < 32 && lpr * 4 < npairs) lpr *= 2;
+    if (D > 4) lpr = 32;
+    const int cpl = (npairs + lpr - 1) / lpr;
+    if (lpr == 8) { if (cpl <= 1) RVGP_V2(8, 1); else if (cpl <= 2) RVGP_V2(8, 2); else RVGP_V2(8, 4); }
+    else if (lpr == 16) { if (cpl <= 1) RVGP_V2(16, 1); else RVGP_V2(16, 2); }
+    else RVGP_V2(32, 1);
+#undef RVGP_V2
+    RVGP_LAUNCH_OK(h, "bsr_spmm_v2_kernel");
+    return RVGP_OK;
+}
+
 template <int D, bool PATTERN>
 static int launch_spmm_d(Handle* h, int nbrows, const int* indptr, const int* indices, const double* vals,
                          const double* X, int64_t ldx, const double* W, int64_t ldw, double* Y, int64_t ldy,
                          int ncols, double alpha, double beta, double gamma) {
-    constexpr int U = (D <= 2) ? 4 : (D <= 3 ? 2 : 1);
     const int rpg = 8;  // rows per lane-group per CTA -> 64 * (32/LPR) consecutive block rows per CTA
 #define RVGP_SPMM_LAUNCH(LPR, CPL)                                                                     \
     do {                                                                                               \
+        constexpr int U = (D * CPL <= 2) ? 4 : ((D * CPL <= 8) ? 2 : 1);                               \
         const int rows_per_cta = 8 * (32 / LPR) * rpg;                                                 \
         const int grid = cdiv(nbrows, rows_per_cta);                                                   \
         bsr_spmm_kernel<D, LPR, CPL, U, PATTERN><<<grid, 256, 0, h->stream>>>(                         \
             nbrows, indptr, indices, vals, X, ldx, W, ldw, Y, ldy, ncols, alpha, beta, gamma, rpg);    \
     } while (0)
-    if (ncols <= 8) RVGP_SPMM_LAUNCH(8, 1);
-    else if (ncols <= 16) RVGP_SPMM_LAUNCH(16, 1);
-    else if (ncols <= 32) RVGP_SPMM_LAUNCH(32, 1);
-    else RVGP_SPMM_LAUNCH(32, 2);
+    // ncu (profiles/r01): a warp-wide 64-bit load costs 2 L1 data-pipe wavefronts even when every lane reads the same
+    // address, so the per-entry block values dominate when 32 lanes share one block row.  With LPR = 8 four block rows
+    // share a warp: value / index loads are amortised over four entries and each lane carries ncols/8 columns.
+    int lpr = h->spmm_lpr;
+    if (lpr != 8 && lpr != 16 && lpr != 32) lpr = (ncols <= 8 * 8 && D <= 4) ? 8 : 32;
+    while (lpr < 32 && lpr * 8 < ncols) lpr *= 2;
+    if (D > 4 && lpr < 32 && ncols > lpr * 2) lpr = (ncols <= 32) ? 16 : 32;     // register budget
+    const int cpl = (ncols + lpr - 1) / lpr;
+    if (lpr == 8) {
+        if (cpl <= 1) RVGP_SPMM_LAUNCH(8, 1); else if (cpl <= 2) RVGP_SPMM_LAUNCH(8, 2);
+        else if (cpl <= 4) RVGP_SPMM_LAUNCH(8, 4); else RVGP_SPMM_LAUNCH(8, 8);
+    } else if (lpr == 16) {
+        if (cpl <= 1) RVGP_SPMM_LAUNCH(16, 1); else if (cpl <= 2) RVGP_SPMM_LAUNCH(16, 2);
+        else RVGP_SPMM_LAUNCH(16, 4);
+    } else {
+        if (cpl <= 1) RVGP_SPMM_LAUNCH(32, 1); else RVGP_SPMM_LAUNCH(32, 2);
+    }
 #undef RVGP_SPMM_LAUNCH
     RVGP_LAUNCH_OK(h, "bsr_spmm_kernel");
     return RVGP_OK;
@@ -121,9 +266,21 @@ static int spmm_dispatch(Handle* h, int nbrows, int d, const int* indptr, const 
     RVGP_REQUIRE(h, gamma == 0.0 || W != nullptr, "spmm: W required when gamma != 0");
     RVGP_REQUIRE(h, Y != X && Y != W, "spmm: Y must not alias X or W");
     if (nbrows == 0) return RVGP_OK;
+    const bool aligned = (ncols % 2 == 0) && (ldx % 2 == 0) && (ldy % 2 == 0) && (W == nullptr || ldw % 2 == 0) &&
+                         ((uintptr_t)X % 16 == 0) && ((uintptr_t)Y % 16 == 0) && ((uintptr_t)W % 16 == 0) &&
+                         (vals == nullptr || (uintptr_t)vals % 16 == 0) && !h->spmm_v1;
     if (vals == nullptr) {
         RVGP_REQUIRE(h, d == 1, "spmm: pattern mode (vals == NULL) needs d == 1");
+        if (aligned) return launch_spmm_v2<1, true>(h, nbrows, indptr, indices, vals, X, ldx, W, ldw, Y, ldy, ncols, alpha, beta, gamma);
         return launch_spmm_d<1, true>(h, nbrows, indptr, indices, vals, X, ldx, W, ldw, Y, ldy, ncols, alpha, beta, gamma);
+    }
+    if (aligned) {
+        switch (d) {
+#define RVGP_CASE(DD) case DD: return launch_spmm_v2<DD, false>(h, nbrows, indptr, indices, vals, X, ldx, W, ldw, Y, ldy, ncols, alpha, beta, gamma);
+            RVGP_CASE(1) RVGP_CASE(2) RVGP_CASE(3) RVGP_CASE(4) RVGP_CASE(5) RVGP_CASE(6) RVGP_CASE(7) RVGP_CASE(8)
+#undef RVGP_CASE
+            default: break;
+        }
     }
     switch (d) {
 #define RVGP_CASE(DD) case DD: return launch_spmm_d<DD, false>(h, nbrows, indptr, indices, vals, X, ldx, W, ldw, Y, ldy, ncols, alpha, beta, gamma);
@@ -144,12 +301,42 @@ extern "C" int rvgp_bsr_spmm_f64(rvgp_handle_t hh, int nbrows, int d, const int3
     return spmm_dispatch(h, nbrows, d, indptr, indices, vals, X, ldx, W, ldw, Y, ldy, ncols, alpha, beta, gamma);
 }
 
+namespace rvgp {
+int spmm_tiled_dispatch(Handle* h, int nbrows, int d, int TR, int ucap, int umax, int nemax, const int* indptr,
+                        const int* tile_u, const int* ucols, const unsigned short* lidx, const double* vals,
+                        const double* X, int64_t ldx, const double* W, int64_t ldw, double* Y, int64_t ldy, int ncols,
+                        double alpha, double beta, double gamma);
+}
+
 // Scaled Chebyshev filter (Zhou & Saad, "A Chebyshev-Davidson algorithm", Alg. 3.1 form):
 //   e = (hi - lo_cut)/2, c = (hi + lo_cut)/2, sigma_1 = e / (lo_spec - c), tau = 2 / sigma_1
 //   Y_1     = (A V - c V) * sigma_1 / e
 //   Y_{i+1} = 2 sigma_{i+1}/e (A Y_i - c Y_i) - sigma_i sigma_{i+1} Y_{i-1},   sigma_{i+1} = 1/(tau - sigma_i)
 // Every step is ONE fused SpMM launch.  The three block vectors rotate; the result is copied back into V
 // when it does not land there.
+template <class Apply>
+static int cheb_recurrence(Handle* h, Apply&& apply, int64_t nrows, double* buf[3], int64_t ld[3], int ncols, int degree,
+                           double lo_spec, double lo_cut, double hi, int* result_slot) {
+    const double e = 0.5 * (hi - lo_cut), c = 0.5 * (hi + lo_cut);
+    const double sigma1 = e / (lo_spec - c), tau = 2.0 / sigma1;
+    double sigma = sigma1;
+    int rc = apply(buf[0], ld[0], (const double*)nullptr, (int64_t)0, buf[1], ld[1], sigma1 / e, -c * sigma1 / e, 0.0);
+    if (rc) return rc;
+    int prev = 0, cur = 1;
+    for (int i = 2; i <= degree; ++i) {
+        const double sn = 1.0 / (tau - sigma);
+        const int nxt = 3 - prev - cur;
+        rc = apply(buf[cur], ld[cur], (const double*)buf[prev], ld[prev], buf[nxt], ld[nxt], 2.0 * sn / e, -2.0 * sn * c / e,
+                   -sigma * sn);
+        if (rc) return rc;
+        sigma = sn;
+        prev = cur;
+        cur = nxt;
+    }
+    *result_slot = cur;
+    return RVGP_OK;
+}
+
 extern "C" int rvgp_cheb_filter_f64(rvgp_handle_t hh, int nbrows, int d, const int32_t* indptr, const int32_t* indices,
                                     const double* vals, double* V, int64_t ldv, double* work0, double* work1,
                                     int64_t ldw, int ncols, int degree, double lo_spec, double lo_cut, double hi) {
@@ -157,29 +344,47 @@ extern "C" int rvgp_cheb_filter_f64(rvgp_handle_t hh, int nbrows, int d, const i
     RVGP_REQUIRE(h, degree >= 0, "cheb_filter: degree >= 0");
     RVGP_REQUIRE(h, hi > lo_cut && lo_cut > lo_spec, "cheb_filter: need lo_spec < lo_cut < hi");
     if (degree == 0 || nbrows == 0) return RVGP_OK;
-    const double e = 0.5 * (hi - lo_cut), c = 0.5 * (hi + lo_cut);
-    const double sigma1 = e / (lo_spec - c), tau = 2.0 / sigma1;
-    double sigma = sigma1;
     double* buf[3] = {V, work0, work1};
     int64_t ld[3] = {ldv, ldw, ldw};
-    int rc = spmm_dispatch(h, nbrows, d, indptr, indices, vals, buf[0], ld[0], nullptr, 0, buf[1], ld[1], ncols,
-                           sigma1 / e, -c * sigma1 / e, 0.0);
+    int slot = 0;
+    auto apply = [&](const double* X, int64_t ldx, const double* W, int64_t ldw_, double* Y, int64_t ldy, double a, double b,
+                     double g) { return spmm_dispatch(h, nbrows, d, indptr, indices, vals, X, ldx, W, ldw_, Y, ldy, ncols, a, b, g); };
+    int rc = cheb_recurrence(h, apply, (int64_t)nbrows * d, buf, ld, ncols, degree, lo_spec, lo_cut, hi, &slot);
     if (rc) return rc;
-    int prev = 0, cur = 1;
-    for (int i = 2; i <= degree; ++i) {
-        const double sn = 1.0 / (tau - sigma);
-        const int nxt = 3 - prev - cur;
-        rc = spmm_dispatch(h, nbrows, d, indptr, indices, vals, buf[cur], ld[cur], buf[prev], ld[prev], buf[nxt],
-                           ld[nxt], ncols, 2.0 * sn / e, -2.0 * sn * c / e, -sigma * sn);
-        if (rc) return rc;
-        sigma = sn;
-        prev = cur;
-        cur = nxt;
-    }
-    if (cur != 0) {
-        RVGP_CUDA_OK(h, cudaMemcpy2DAsync(V, ldv * sizeof(double), buf[cur], ld[cur] * sizeof(double),
+    if (slot != 0) {
+        RVGP_CUDA_OK(h, cudaMemcpy2DAsync(V, ldv * sizeof(double), buf[slot], ld[slot] * sizeof(double),
                                           (size_t)ncols * sizeof(double), (size_t)nbrows * d,
                                           cudaMemcpyDeviceToDevice, h->stream));
     }
+    return RVGP_OK;
+}
+
+// Same filter through the shared-memory-staged SpMM (rvgp_bsr_spmm_tiled_f64).  The panel is first copied into a
+// CONTIGUOUS scratch panel so that every staged neighbour is one bulk copy of d*ncols*8 bytes; work0..work2 are three
+// (nrows x ncols) contiguous scratch panels.
+extern "C" int rvgp_cheb_filter_tiled_f64(rvgp_handle_t hh, int nbrows, int d, int TR, int ucap, int umax, int nemax,
+                                          const int32_t* indptr, const int32_t* tile_u, const int32_t* ucols,
+                                          const uint16_t* lidx, const double* vals, double* V, int64_t ldv, double* work0,
+                                          double* work1, double* work2, int ncols, int degree, double lo_spec,
+                                          double lo_cut, double hi) {
+    Handle* h = H(hh);
+    RVGP_REQUIRE(h, degree >= 0, "cheb_filter: degree >= 0");
+    RVGP_REQUIRE(h, hi > lo_cut && lo_cut > lo_spec, "cheb_filter: need lo_spec < lo_cut < hi");
+    if (degree == 0 || nbrows == 0) return RVGP_OK;
+    const int64_t nrows = (int64_t)nbrows * d;
+    RVGP_CUDA_OK(h, cudaMemcpy2DAsync(work0, (size_t)ncols * sizeof(double), V, ldv * sizeof(double),
+                                      (size_t)ncols * sizeof(double), (size_t)nrows, cudaMemcpyDeviceToDevice, h->stream));
+    double* buf[3] = {work0, work1, work2};
+    int64_t ld[3] = {ncols, ncols, ncols};
+    int slot = 0;
+    auto apply = [&](const double* X, int64_t ldx, const double* W, int64_t ldw_, double* Y, int64_t ldy, double a, double b,
+                     double g) {
+        return spmm_tiled_dispatch(h, nbrows, d, TR, ucap, umax, nemax, indptr, tile_u, ucols, lidx, vals, X, ldx, W, ldw_, Y,
+                                   ldy, ncols, a, b, g);
+    };
+    int rc = cheb_recurrence(h, apply, nrows, buf, ld, ncols, degree, lo_spec, lo_cut, hi, &slot);
+    if (rc) return rc;
+    RVGP_CUDA_OK(h, cudaMemcpy2DAsync(V, ldv * sizeof(double), buf[slot], (size_t)ncols * sizeof(double),
+                                      (size_t)ncols * sizeof(double), (size_t)nrows, cudaMemcpyDeviceToDevice, h->stream));
     return RVGP_OK;
 }

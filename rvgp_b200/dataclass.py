@@ -60,7 +60,8 @@ class data:
                  n_eigenpairs=None,
                  device=None,
                  eig_tol=1e-12,
-                 verbose=True):
+                 verbose=True,
+                 shard=None):
         say = print if verbose else (lambda *a, **k: None)
         self._duals = {}
         self.timings = {}
@@ -72,6 +73,16 @@ class data:
             torch.cuda.synchronize(dev)
             return time.perf_counter()
 
+        # multi-GPU: one process per GPU (torch.distributed); kNN queries and the eigensolver are row-sharded,
+        # everything else is replicated
+        import torch.distributed as dist
+        world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        if shard is None:
+            shard = world > 1
+        shard = bool(shard) and world > 1
+        rank = dist.get_rank() if shard else 0
+        self.sharded = shard
+
         t0 = tick()
         Xd = geo.to_device_f64(vertices, dev)
         n, D = Xd.shape
@@ -79,7 +90,15 @@ class data:
 
         say('Fit graph')
         t0 = tick()
-        graph = geo.manifold_graph(Xd, n_neighbors=n_neighbors, device=dev)
+        if shard:
+            q0, q1 = (n * rank) // world, (n * (rank + 1)) // world
+            knn_loc = geo.knn_device(Xd, n_neighbors, q0, q1 - q0)
+            from .distributed import Comm
+            knn = Comm().allgather_rows(knn_loc, [(n * (r + 1)) // world - (n * r) // world for r in range(world)])
+            indptr, indices = geo.knn_to_csr_device(knn)
+            graph = geo.ManifoldGraph(indptr, indices, X=Xd, knn=knn)
+        else:
+            graph = geo.manifold_graph(Xd, n_neighbors=n_neighbors, device=dev)
         self.timings["graph"] = tick() - t0
 
         say('Fit tangent spaces')
@@ -127,13 +146,31 @@ class data:
         k_Lc = N_Lc if (n_eigenpairs is None or n_eigenpairs >= N_Lc) else n_eigenpairs
         hi = 2.0 * (max_row - 1)
         t0 = tick()
-        st_L = {}
-        evals_L, U_L_p = smallest_eigenpairs(A_L, k_L, upper_bound=hi, tol=eig_tol, stats=st_L)
-        self.timings["eig_L"] = tick() - t0
-        t0 = tick()
-        st_Lc = {}
-        evals_Lc, U_Lc_p = smallest_eigenpairs(A_Lc, k_Lc, upper_bound=hi, tol=eig_tol, stats=st_Lc)
-        self.timings["eig_Lc"] = tick() - t0
+        st_L, st_Lc = {}, {}
+        if shard:
+            from .distributed import HaloPlan, ShardedBsr, Comm, partition_rows
+            comm = Comm()
+            bounds = partition_rows(p_indptr.cpu().numpy(), world)
+            plan = HaloPlan(p_indptr, p_indices, bounds, rank)
+            plan.exchange_requests()
+            S_L = ShardedBsr(plan, 1, None, comm)
+            S_Lc = ShardedBsr(plan, dim_man, Lc_vals_p[plan.e0:plan.e1].contiguous(), comm)
+            counts = [int(bounds[r + 1] - bounds[r]) for r in range(world)]
+            self.stats["halo"] = dict(n_loc=plan.n_loc, n_halo=plan.n_halo, send=sum(plan.send_counts))
+            evals_L, U_loc = smallest_eigenpairs(S_L, k_L, upper_bound=hi, tol=eig_tol, stats=st_L, comm=comm)
+            U_L_p = comm.allgather_rows(U_loc, counts)
+            self.timings["eig_L"] = tick() - t0
+            t0 = tick()
+            evals_Lc, U_loc = smallest_eigenpairs(S_Lc, k_Lc, upper_bound=hi, tol=eig_tol, stats=st_Lc, comm=comm)
+            U_Lc_p = comm.allgather_rows(U_loc, [c * dim_man for c in counts])
+            del U_loc
+            self.timings["eig_Lc"] = tick() - t0
+        else:
+            evals_L, U_L_p = smallest_eigenpairs(A_L, k_L, upper_bound=hi, tol=eig_tol, stats=st_L)
+            self.timings["eig_L"] = tick() - t0
+            t0 = tick()
+            evals_Lc, U_Lc_p = smallest_eigenpairs(A_Lc, k_Lc, upper_bound=hi, tol=eig_tol, stats=st_Lc)
+            self.timings["eig_Lc"] = tick() - t0
         self.stats["eig_L"], self.stats["eig_Lc"] = st_L, st_Lc
 
         t0 = tick()

@@ -43,6 +43,65 @@ class BsrMatrix:
                int(ncols), float(alpha), float(beta), float(gamma))
         return Y
 
+    # ---- shared-memory-staged variant (K9 v2) ---------------------------------------------------------
+    def build_plan(self, TR, ucap=None, h=None):
+        """Tile plan for rvgp_bsr_spmm_tiled_f64; returns the plan dict or None when the pattern is not local
+        enough (then the gather kernel keeps being used)."""
+        key = int(TR)
+        plans = self.__dict__.setdefault("_plans", {})
+        if key in plans:
+            return plans[key]
+        h = h or get_handle(self.indptr.device.index)
+        dev = self.indptr.device
+        if ucap is None:
+            ucap = min(1024, 16 * TR)
+        ntiles = (self.nbrows + TR - 1) // TR
+        tile_u = torch.empty(ntiles, dtype=torch.int32, device=dev)
+        ucols = torch.empty(ntiles * ucap, dtype=torch.int32, device=dev)
+        lidx = torch.empty(max(1, self.nnzb), dtype=torch.int16, device=dev)
+        info = torch.zeros(3, dtype=torch.int32, device=dev)
+        h.call("rvgp_bsr_tile_plan", self.nbrows, self.indptr, self.indices, int(TR), int(ucap), tile_u, ucols, lidx, info)
+        umax, invalid, nemax = [int(v) for v in info.cpu().tolist()]
+        plan = None
+        if not invalid:
+            # shared memory is sized for the 97th percentile of unique neighbours per tile; the few heavier tiles
+            # (Morton-curve jumps) gather from global memory inside the same kernel
+            tu = tile_u.cpu().numpy()
+            usoft = int(min(umax, (int(np.percentile(tu, 97)) + 3) // 4 * 4))
+            plan = dict(TR=int(TR), ucap=int(ucap), umax=umax, usoft=usoft, nemax=nemax, tile_u=tile_u, ucols=ucols,
+                        lidx=lidx, umean=float(tu.mean()), heavy_frac=float((tu > usoft).mean()))
+        plans[key] = plan
+        return plan
+
+    def tiled_smem_bytes(self, plan, ncols):
+        d = self.d
+        return (32 + plan["usoft"] * d * ncols * 8 + (plan["nemax"] * d * d * 8 if self.vals is not None else 0)
+                + ((plan["nemax"] + 7) // 8 * 8) * 2 + plan["ucap"] * 4)
+
+    def choose_plan(self, ncols, budget=100 * 1024, h=None):
+        """Largest tile whose staged working set leaves >= 2 CTAs per SM."""
+        for TR in (64, 32, 16, 8):
+            plan = self.build_plan(TR, h=h)
+            if plan is not None and self.tiled_smem_bytes(plan, ncols) <= budget:
+                return plan
+        return None
+
+    def spmm_tiled(self, plan, X, Y, alpha=1.0, beta=0.0, gamma=0.0, W=None, h=None):
+        h = h or get_handle(X.device.index)
+        h.call("rvgp_bsr_spmm_tiled_f64", self.nbrows, self.d, plan["TR"], plan["ucap"], plan["usoft"], plan["nemax"],
+               self.indptr, plan["tile_u"], plan["ucols"], plan["lidx"], self.vals, X, I64(X.stride(0)), W,
+               I64(W.stride(0) if W is not None else 0), Y, I64(Y.stride(0)), int(X.shape[1]), float(alpha),
+               float(beta), float(gamma))
+        return Y
+
+    row_offset = 0          # global row of local row 0 (non-zero only for row-sharded operators)
+
+    def cheb_filter(self, Vp, w0, w1, ncols, degree, lo_spec, lo_cut, hi, h=None):
+        """Degree-`degree` Chebyshev filter of the panel Vp in place; the whole recurrence runs inside one C call."""
+        h = h or get_handle(Vp.device.index)
+        h.call("rvgp_cheb_filter_f64", self.nbrows, self.d, self.indptr, self.indices, self.vals, Vp, I64(Vp.stride(0)),
+               w0, w1, I64(w0.stride(0)), int(ncols), int(degree), float(lo_spec), float(lo_cut), float(hi))
+
     def matmat(self, X, out=None, h=None):
         """out = A @ X for any number of columns (panels of <= 64)."""
         if out is None:
@@ -61,10 +120,11 @@ def _dgemm(h, m, n, k, A, lda, a_kmajor, B, ldb, b_kmajor, C, ldc, alpha=1.0, sc
 class _Dense:
     """Tall-skinny FP64 products on (N x m) block vectors."""
 
-    def __init__(self, h, N, m, device):
-        self.h, self.N, self.m = h, N, m
+    def __init__(self, h, N, m, device, comm=None):
+        self.h, self.N, self.m, self.comm = h, N, m, comm
         tiles = math.ceil(m / 128) ** 2
         self.split = max(1, min(64, (2 * h.sm_count) // tiles, N // 2048 if N >= 4096 else 1))
+        self.red_rows = N
         self.ws = torch.empty(self.split * m * m, dtype=torch.float64, device=device)
         nred = h.query("rvgp_coldot_workspace_bytes", I64(N), int(m)) // 8
         self.red_ws = torch.empty(max(1, nred), dtype=torch.float64, device=device)
@@ -75,6 +135,8 @@ class _Dense:
         m1, m2 = V.shape[1], W.shape[1]
         _dgemm(self.h, m1, m2, self.N, V, V.stride(0), 0, W, W.stride(0), 0, out, out.stride(0),
                split_k=self.split, ws=self.ws)
+        if self.comm is not None:
+            self.comm.allreduce_(out)            # row-sharded: sum of the ranks' partial Gram matrices
         return out
 
     def apply(self, V, Cm, out):
@@ -87,12 +149,16 @@ class _Dense:
         out = self.small[: A.shape[1]]
         self.h.call("rvgp_coldot_f64", I64(self.N), int(A.shape[1]), A, I64(A.stride(0)), B, I64(B.stride(0)),
                     out, self.red_ws)
+        if self.comm is not None:
+            self.comm.allreduce_(out)
         return out
 
     def resid_sq(self, W, V, theta):
         out = self.small[: V.shape[1]]
         self.h.call("rvgp_resid_sq_f64", I64(self.N), int(V.shape[1]), W, I64(W.stride(0)), V, I64(V.stride(0)),
                     theta, out, self.red_ws)
+        if self.comm is not None:
+            self.comm.allreduce_(out)
         return out
 
     def colscale(self, A, s):
@@ -100,7 +166,7 @@ class _Dense:
 
 
 def smallest_eigenpairs(A, k, upper_bound, lower_bound=0.0, tol=1e-12, nex=None, seed=0, max_outer=80,
-                        cond_max=1e6, deg0=20, panel=None, stats=None, verbose=False):
+                        cond_max=1e6, deg0=20, panel=None, stats=None, verbose=False, comm=None):
     """Smallest k eigenpairs of the symmetric PSD BsrMatrix ``A``.
 
     upper_bound: a rigorous upper bound of the spectrum (2 * max degree for (connection) Laplacians).
@@ -109,15 +175,22 @@ def smallest_eigenpairs(A, k, upper_bound, lower_bound=0.0, tol=1e-12, nex=None,
     """
     dev = A.indptr.device
     h = get_handle(dev.index)
-    N = A.nrows
-    k = int(min(k, N))
+    N = A.nrows                       # LOCAL rows (== global rows on a single GPU)
+    Nglob = N
+    if comm is not None and comm.world > 1:
+        t = torch.tensor([N], dtype=torch.int64, device=dev)
+        comm.allreduce_(t)
+        Nglob = int(t.item())
+    else:
+        comm = None
+    k = int(min(k, Nglob))
     if nex is None:
         nex = max(16, int(math.ceil(0.2 * k)))
-    m = min(N, k + nex)
+    m = min(Nglob, k + nex)
     if panel is None:
         panel = 64 if m >= 128 else 32
-    if m < N:
-        m = min(N, ((m + panel - 1) // panel) * panel)
+    if m < Nglob:
+        m = min(Nglob, ((m + panel - 1) // panel) * panel)
     hi = float(upper_bound)
     lo_spec = float(lower_bound)
     tol_abs = tol * hi
@@ -133,10 +206,10 @@ def smallest_eigenpairs(A, k, upper_bound, lower_bound=0.0, tol=1e-12, nex=None,
     Hd = torch.empty((m, m), dtype=torch.float64, device=dev)
     Cd = torch.empty((m, m), dtype=torch.float64, device=dev)
     theta_d = torch.empty(m, dtype=torch.float64, device=dev)
-    dense = _Dense(h, N, m, dev)
+    dense = _Dense(h, N, m, dev, comm)
 
     V, W = B1, B2
-    h.call("rvgp_fill_uniform_f64", I64(N), int(m), V, I64(V.stride(0)), U64(seed), I64(0))
+    h.call("rvgp_fill_uniform_f64", I64(N), int(m), V, I64(V.stride(0)), U64(seed), I64(0), I64(A.row_offset))
 
     deg = np.full(m, deg0, dtype=np.int64)
     a_cut = lo_spec + 0.3 * (hi - lo_spec)
@@ -153,9 +226,7 @@ def smallest_eigenpairs(A, k, upper_bound, lower_bound=0.0, tol=1e-12, nex=None,
             dg = int(deg[p0:p1].max())
             if dg <= 0:
                 continue
-            Vp = V[:, p0:p1]
-            h.call("rvgp_cheb_filter_f64", A.nbrows, A.d, A.indptr, A.indices, A.vals, Vp, I64(V.stride(0)),
-                   w0, w1, I64(panel), int(p1 - p0), dg, lo_spec, float(a_cut), hi)
+            A.cheb_filter(V[:, p0:p1], w0, w1, p1 - p0, dg, lo_spec, float(a_cut), hi, h=h)
             st["spmm_launches"] += dg
             st["filter_launches"] += dg
             st["filter_col_degrees"] += dg * (p1 - p0)
@@ -209,11 +280,11 @@ def smallest_eigenpairs(A, k, upper_bound, lower_bound=0.0, tol=1e-12, nex=None,
         st["outer"] = it + 1
 
         nconv = int((res[:k] <= tol_abs).sum())
-        a_cut = float(theta[-1]) if m < N else a_cut
+        a_cut = float(theta[-1]) if m < Nglob else a_cut
         if verbose:
             print("  [eig] it %d  cut=%.6g  conv=%d/%d  maxres=%.3e  theta_k=%.9g" %
                   (it, a_cut, nconv, k, res[:k].max(), theta[k - 1]))
-        if nconv == k or m >= N:
+        if nconv == k or m >= Nglob:
             break
         a_cut = max(a_cut, lo_spec + 1e-12 * (hi - lo_spec) + theta[k - 1] * (1 + 1e-9))
         deg = _next_degrees(theta, res, k, tol_abs, a_cut, hi, lo_spec, cond_max)

@@ -18,6 +18,7 @@ from sklearn.model_selection import train_test_split
 
 from . import params as P
 from .geometry import furthest_point_sampling, gather_rows_device, to_device_f64  # noqa: F401
+from ._cabi import RvgpError
 from .gp import DeviceGPR
 from .kernels import ManifoldKernel
 
@@ -79,8 +80,18 @@ class manifold_GPR:
     def _loss_and_grad(self, u, plist):
         for p, ui in zip(plist, u):
             p.unconstrained = float(ui)
-        S, dS = self.kernel.eval_S(typ=self.kernel.typ, grads=True)
-        lml, gS, gnoise = self._gpr.lml_and_grads(S, self.likelihood.variance.value, grads=True)
+        try:
+            with np.errstate(all="ignore"):
+                S, dS = self.kernel.eval_S(typ=self.kernel.typ, grads=True)
+                if not np.all(np.isfinite(S)) or np.any(S <= 0):
+                    raise FloatingPointError("non-finite spectral density")
+                lml, gS, gnoise = self._gpr.lml_and_grads(S, self.likelihood.variance.value, grads=True)
+                if not (np.isfinite(lml) and np.all(np.isfinite(gS)) and np.isfinite(gnoise)):
+                    raise FloatingPointError("non-finite LML")
+        except (FloatingPointError, RvgpError):
+            # a trial point of the line search left the domain (non-finite density / non-SPD Gram): report a huge
+            # loss so L-BFGS-B backs off (TensorFlow would raise here and abort the fit)
+            return 1e50, np.zeros(len(plist))
         g = []
         for p in plist:
             if p is self.likelihood.variance:

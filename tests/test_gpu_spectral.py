@@ -121,8 +121,11 @@ def test_column_reductions_and_utils():
     h.call("rvgp_colscale_f64", I64(N), m, Ad, I64(m), thd)
     np.testing.assert_allclose(Ad.cpu().numpy(), A * th, rtol=1e-15)
     F1 = torch.empty((N, m), dtype=torch.float64, device=_dev()); F2 = torch.empty((N, 10), dtype=torch.float64, device=_dev())
-    h.call("rvgp_fill_uniform_f64", I64(N), m, F1, I64(m), U64(7), I64(0))
-    h.call("rvgp_fill_uniform_f64", I64(N), 10, F2, I64(10), U64(7), I64(20))
+    h.call("rvgp_fill_uniform_f64", I64(N), m, F1, I64(m), U64(7), I64(0), I64(0))
+    h.call("rvgp_fill_uniform_f64", I64(N), 10, F2, I64(10), U64(7), I64(20), I64(0))
+    F3 = torch.empty((100, m), dtype=torch.float64, device=_dev())
+    h.call("rvgp_fill_uniform_f64", I64(100), m, F3, I64(m), U64(7), I64(0), I64(5000))
+    assert np.array_equal(F3.cpu().numpy(), F1.cpu().numpy()[5000:5100])      # row-sharding invariant
     f1 = F1.cpu().numpy()
     assert np.array_equal(f1[:, 20:30], F2.cpu().numpy())          # counter based: depends on (seed,row,col) only
     assert abs(f1.mean()) < 0.01 and f1.min() >= -1 and f1.max() < 1 and abs(f1.std() - 3 ** -0.5) < 0.01
@@ -158,3 +161,42 @@ def test_eigensolver_matches_reference_arpack(case):
             Phi, ref = U * np.sqrt(n), g["evecs_L"]
         for s in eigen_clusters(ev_ref)[:-1]:
             assert subspace_angle_max(Phi[:, s], ref[:, s]) < 1e-6, (which, s)
+
+
+@pytest.mark.parametrize("case", ["sphere_n2000_k50", "flat3torus_R6_n900_k24", "torus_n600_k20"])
+@pytest.mark.parametrize("ncols", [2, 16, 32, 50, 64])
+@pytest.mark.parametrize("TR", [8, 16, 32])
+def test_spmm_tiled_matches_scipy(case, ncols, TR):
+    """K9 v2 (TMA-staged tiles) against SciPy, on matrices in their ORIGINAL (non-local) order as well: the plan only
+    needs ucap to hold the tile's unique neighbours."""
+    g = load_golden(case)
+    for which in ("Lc", "L"):
+        A, S = _bsr_from_golden(g, which)
+        plan = A.build_plan(TR, ucap=min(1024, 40 * TR))
+        assert plan is not None
+        if A.tiled_smem_bytes(plan, ncols) > 200 * 1024:
+            continue
+        rng = np.random.default_rng(2)
+        X = rng.normal(size=(A.nrows, ncols)); W = rng.normal(size=(A.nrows, ncols))
+        Xd, Wd = torch.from_numpy(X).to(_dev()), torch.from_numpy(W).to(_dev())
+        Yd = torch.full_like(Xd, 7.0)
+        A.spmm_tiled(plan, Xd, Yd)
+        ref = S @ X
+        assert np.abs(Yd.cpu().numpy() - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max())
+        A.spmm_tiled(plan, Xd, Yd, alpha=0.7, beta=-1.3, gamma=0.25, W=Wd)
+        ref2 = 0.7 * ref - 1.3 * X + 0.25 * W
+        assert np.abs(Yd.cpu().numpy() - ref2).max() <= 1e-13 * max(1.0, np.abs(ref2).max())
+        # strided input (panel view of a wider block vector): non-contiguous staging path
+        big = torch.zeros((A.nrows, 2 * ncols + 6), dtype=torch.float64, device=_dev())
+        big[:, 4:4 + ncols] = Xd
+        A.spmm_tiled(plan, big[:, 4:4 + ncols], Yd)
+        assert np.abs(Yd.cpu().numpy() - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max())
+
+
+def test_spmm_tiled_rejects_unaligned():
+    g = load_golden("torus_n600_k20")
+    A, S = _bsr_from_golden(g, "Lc")
+    plan = A.build_plan(16, ucap=640)
+    X = torch.zeros((A.nrows, 7), dtype=torch.float64, device=_dev())
+    with pytest.raises(ValueError):
+        A.spmm_tiled(plan, X, torch.empty_like(X))

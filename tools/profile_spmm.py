@@ -44,6 +44,33 @@ def main():
                 ms = e0.elapsed_time(e1) / reps
                 by = M.spmm_bytes(b, fused=fused)
                 out["%s_b%d_%s" % (name, b, "fused" if fused else "plain")] = dict(ms=round(ms, 4), GBs=round(by / ms / 1e6, 1), frac=round(by / ms / 1e6 / 6534.5, 3))
+    # shared-memory-staged variant
+    for name, M in (("Lc", A), ("L", L)):
+        for TR in (8, 16, 32):
+            plan = M.build_plan(TR)
+            if plan is None:
+                out["%s_TR%d" % (name, TR)] = "plan invalid"; continue
+            for b in (32, 64):
+                smem = M.tiled_smem_bytes(plan, b)
+                if smem > 200 * 1024:
+                    continue
+                X = torch.randn((M.nrows, b), dtype=torch.float64, device=dev)
+                W = torch.randn((M.nrows, b), dtype=torch.float64, device=dev)
+                Y = torch.empty_like(X); Y2 = torch.empty_like(X)
+                kw = dict(alpha=0.7, beta=-0.2, gamma=0.1, W=W)
+                M.spmm(X, Y2, **kw)
+                for _ in range(3):
+                    M.spmm_tiled(plan, X, Y, **kw)
+                torch.cuda.synchronize()
+                err = float((Y - Y2).abs().max())
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(reps):
+                    M.spmm_tiled(plan, X, Y, **kw)
+                e1.record(); torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / reps
+                by = M.spmm_bytes(b, fused=True)
+                out["%s_TR%d_b%d_tiled_fused" % (name, TR, b)] = dict(ms=round(ms, 4), GBs=round(by / ms / 1e6, 1), frac=round(by / ms / 1e6 / 6534.5, 3), umax=plan["umax"], usoft=plan["usoft"], umean=round(plan["umean"],1), heavy=round(plan["heavy_frac"],4), nemax=plan["nemax"], smem=smem, maxerr=err)
     print(json.dumps(out, indent=1))
 
 if __name__ == "__main__":

@@ -54,6 +54,13 @@ int rvgp_bsr_spmm_f64(rvgp_handle_t h, int nbrows, int d, const int32_t* indptr,
                       const double* vals, const double* X, int64_t ldx, const double* W, int64_t ldw,
                       double* Y, int64_t ldy, int ncols, double alpha, double beta, double gamma);
 
+/* ROT2 storage for d == 2: when every block is a scaled 2x2 orthogonal matrix [[a,-s*b],[b,s*a]] (true for the
+ * connection Laplacian: Procrustes blocks, diagonal deg*I) it is stored as (a,b) with s in the sign bit of the column
+ * index -- half the matrix bytes and half the value loads.  bad_flag (device int32): bit0 set if some block does not
+ * fit within rtol.  Use the outputs with rvgp_bsr_spmm_f64 / rvgp_cheb_filter_f64 by passing d = -2. */
+int rvgp_bsr_compress_rot2(rvgp_handle_t h, int64_t nnzb, const double* vals, const int32_t* indices, double* ab,
+                           int32_t* idx_flag, int32_t* bad_flag, double rtol);
+
 /* Chebyshev filter of degree `degree` applied in place to the ncols columns of V (scaled three-term
  * recurrence, Zhou & Saad): damps [lo_cut, hi] and amplifies below lo_cut, normalised at `lo_spec`.
  * work0, work1: two (nrows x ncols) scratch block vectors with leading dimension ldw.

@@ -126,6 +126,129 @@ dgemm_kernel(int M, int N, int64_t K, double alpha, const double* __restrict__ A
     }
 }
 
+// ---- DMMA variant: same tiling / loaders, inner product on the FP64 tensor path (mma.sync.m8n8k4.f64) ---------
+// CTA tile 128 x 64 x 16, 8 warps as 4 (m) x 2 (n), warp tile 32 x 32 = 4 x 4 MMA tiles.  Fragment layout (PTX ISA):
+//   A (8x4, row): a0 -> row = lane>>2, k = lane&3      B (4x8, col): b0 -> k = lane&3, n = lane>>2
+//   C/D (8x8):    c0,c1 -> row = lane>>2, cols = 2*(lane&3) + {0,1}
+// (tcgen05 has no FP64 kind; this legacy warp-level MMA is the only FP64 tensor path on sm_100a.)
+constexpr int DBN = 64, DPAD = 8;
+
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+template <bool A_KMAJOR, bool B_KMAJOR>
+__global__ void __launch_bounds__(256, 2)
+dgemm_dmma_kernel(int M, int N, int64_t K, double alpha, const double* __restrict__ A, int64_t lda,
+                  const double* __restrict__ B, int64_t ldb, const double* __restrict__ scale_k,
+                  double* __restrict__ C, int64_t ldc, int split_k, double* __restrict__ ws, double beta, int lower_only) {
+    if (lower_only && blockIdx.x * DBN > blockIdx.y * BM + (BM - 1)) return;
+    __shared__ __align__(16) double As[BK][BM + DPAD];
+    __shared__ __align__(16) double Bs[BK][DBN + DPAD];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int wm = warp >> 1, wn = warp & 1;                 // 4 x 2 warps
+    const int gid = lane >> 2, tig = lane & 3;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * DBN;
+    const int64_t ktiles = (K + BK - 1) / BK;
+    const int64_t tiles_per = (ktiles + split_k - 1) / split_k;
+    const int64_t kt0 = (int64_t)blockIdx.z * tiles_per;
+    const int64_t kt1 = (kt0 + tiles_per < ktiles) ? kt0 + tiles_per : ktiles;
+
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+    double ra[8], rb[4];
+    auto load_tiles = [&](int64_t kt) {
+        const int64_t k0 = kt * BK;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            int i, k;
+            if (A_KMAJOR) { k = t & 15; i = (t >> 4) + 16 * r; }
+            else          { i = t & 127; k = (t >> 7) + 2 * r; }
+            const int64_t gk = k0 + k;
+            const int gi = m0 + i;
+            double v = 0.0;
+            if (gi < M && gk < K) {
+                v = A_KMAJOR ? __ldg(A + (int64_t)gi * lda + gk) : __ldg(A + gk * lda + gi);
+                if (scale_k) v *= __ldg(scale_k + gk);
+            }
+            ra[r] = v;
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            int j, k;
+            if (B_KMAJOR) { k = t & 15; j = (t >> 4) + 16 * r; }
+            else          { j = t & 63; k = (t >> 6) + 4 * r; }
+            const int64_t gk = k0 + k;
+            const int gj = n0 + j;
+            double v = 0.0;
+            if (gj < N && gk < K) v = B_KMAJOR ? __ldg(B + (int64_t)gj * ldb + gk) : __ldg(B + gk * ldb + gj);
+            rb[r] = v;
+        }
+    };
+    auto store_tiles = [&]() {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            int i, k;
+            if (A_KMAJOR) { k = t & 15; i = (t >> 4) + 16 * r; }
+            else          { i = t & 127; k = (t >> 7) + 2 * r; }
+            As[k][i] = ra[r];
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            int j, k;
+            if (B_KMAJOR) { k = t & 15; j = (t >> 4) + 16 * r; }
+            else          { j = t & 63; k = (t >> 6) + 4 * r; }
+            Bs[k][j] = rb[r];
+        }
+    };
+
+    if (kt0 < kt1) load_tiles(kt0);
+    for (int64_t kt = kt0; kt < kt1; ++kt) {
+        store_tiles();
+        __syncthreads();
+        if (kt + 1 < kt1) load_tiles(kt + 1);
+#pragma unroll
+        for (int k4 = 0; k4 < BK; k4 += 4) {
+            double a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[k4 + tig][wm * 32 + i * 8 + gid];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[k4 + tig][wn * 32 + j * 8 + gid];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+        __syncthreads();
+    }
+
+    double* out = C;
+    int64_t ldo = ldc;
+    double sc = alpha;
+    if (split_k > 1) { out = ws + (int64_t)blockIdx.z * M * N; ldo = N; sc = 1.0; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int gi = m0 + wm * 32 + i * 8 + gid;
+        if (gi >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int gj = n0 + wn * 32 + j * 8 + 2 * tig + c;
+                if (gj < N) {
+                    double v = sc * acc[i][j][c];
+                    if (beta != 0.0 && split_k == 1) v = fma(beta, out[(int64_t)gi * ldo + gj], v);
+                    out[(int64_t)gi * ldo + gj] = v;
+                }
+            }
+    }
+}
+
 __global__ void splitk_reduce_kernel(int M, int N, int split_k, double alpha, const double* __restrict__ ws,
                                      double* __restrict__ C, int64_t ldc, double beta) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -231,13 +354,23 @@ int dgemm_launch(Handle* h, int m, int n, int64_t k, double alpha, const double*
     RVGP_REQUIRE(h, m >= 0 && n >= 0 && k >= 0 && split_k >= 1, "dgemm: bad sizes");
     RVGP_REQUIRE(h, split_k == 1 || workspace != nullptr, "dgemm: split_k > 1 needs a workspace");
     if (m == 0 || n == 0) return RVGP_OK;
-    dim3 grid(cdiv(n, BN), cdiv(m, BM), split_k);
-#define RVGP_GEMM(AK, BKM) dgemm_kernel<AK, BKM><<<grid, 256, 0, h->stream>>>(m, n, k, alpha, A, lda, B, ldb, scale_k, C, ldc, split_k, workspace, beta, lower_only)
-    if (a_kmajor && b_kmajor) RVGP_GEMM(true, true);
-    else if (a_kmajor && !b_kmajor) RVGP_GEMM(true, false);
-    else if (!a_kmajor && b_kmajor) RVGP_GEMM(false, true);
-    else RVGP_GEMM(false, false);
+    if (h->dgemm_dmma) {
+        dim3 grid(cdiv(n, DBN), cdiv(m, BM), split_k);
+#define RVGP_GEMM(AK, BKM) dgemm_dmma_kernel<AK, BKM><<<grid, 256, 0, h->stream>>>(m, n, k, alpha, A, lda, B, ldb, scale_k, C, ldc, split_k, workspace, beta, lower_only)
+        if (a_kmajor && b_kmajor) RVGP_GEMM(true, true);
+        else if (a_kmajor && !b_kmajor) RVGP_GEMM(true, false);
+        else if (!a_kmajor && b_kmajor) RVGP_GEMM(false, true);
+        else RVGP_GEMM(false, false);
 #undef RVGP_GEMM
+    } else {
+        dim3 grid(cdiv(n, BN), cdiv(m, BM), split_k);
+#define RVGP_GEMM(AK, BKM) dgemm_kernel<AK, BKM><<<grid, 256, 0, h->stream>>>(m, n, k, alpha, A, lda, B, ldb, scale_k, C, ldc, split_k, workspace, beta, lower_only)
+        if (a_kmajor && b_kmajor) RVGP_GEMM(true, true);
+        else if (a_kmajor && !b_kmajor) RVGP_GEMM(true, false);
+        else if (!a_kmajor && b_kmajor) RVGP_GEMM(false, true);
+        else RVGP_GEMM(false, false);
+#undef RVGP_GEMM
+    }
     RVGP_LAUNCH_OK(h, "dgemm_kernel");
     if (split_k > 1) {
         const int64_t tot = (int64_t)m * n;

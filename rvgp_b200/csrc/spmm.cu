@@ -97,7 +97,12 @@ bsr_spmm_kernel(int nbrows, const int* __restrict__ indptr, const int* __restric
 // capped near 64 B/clk/SM.  Here every lane owns PAIRS of adjacent columns and gathers them with LDG.128 (double2),
 // and even-sized value blocks are read as double2 as well: twice the bytes per wavefront, half the load instructions.
 // Needs even ncols / leading dimensions and 16-byte aligned X, W, Y (the dispatcher falls back to v1 otherwise).
-template <int D, int LPR, int CPL2, int U, bool PATTERN>
+//
+// ROT2 (d == 2 only): every block of the connection Laplacian is a scaled 2x2 orthogonal matrix
+//   [[a, -s*b], [b, s*a]],  s = +-1  (rotation or reflection; the diagonal block is deg * I),
+// so it can be stored as ONE double2 (a, b) with s in the sign bit of the column index: half the matrix bytes and one
+// LDG.128 per stored block instead of two.  Roofline accounting keeps the uncompressed formula.
+template <int D, int LPR, int CPL2, int U, bool PATTERN, bool ROT2>
 __global__ void __launch_bounds__(256)
 bsr_spmm_v2_kernel(int nbrows, const int* __restrict__ indptr, const int* __restrict__ indices,
                    const double* __restrict__ vals, const double* __restrict__ X, int64_t ldx,
@@ -125,8 +130,13 @@ bsr_spmm_v2_kernel(int nbrows, const int* __restrict__ indptr, const int* __rest
 
         for (int e = e0; e < e1; e += U) {
             int j[U];
+            bool flip[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) j[u] = (e + u < e1) ? __ldg(indices + e + u) : -1;
+            for (int u = 0; u < U; ++u) {
+                j[u] = (e + u < e1) ? __ldg(indices + e + u) : -1;
+                flip[u] = false;
+                if (ROT2 && e + u < e1) { flip[u] = j[u] < 0; j[u] &= 0x7fffffff; }
+            }
             double2 x[U][D][CPL2];
 #pragma unroll
             for (int u = 0; u < U; ++u)
@@ -148,9 +158,13 @@ bsr_spmm_v2_kernel(int nbrows, const int* __restrict__ indptr, const int* __rest
                         acc[0][cc].y = fma(r, x[u][0][cc].y, acc[0][cc].y);
                     }
                 } else {
-                    const double* rp = vals + (int64_t)(e + u) * (D * D);
+                    const double* rp = vals + (int64_t)(e + u) * (ROT2 ? 2 : D * D);
                     double r[D * D];
-                    if ((D * D) % 2 == 0) {
+                    if (ROT2) {
+                        const double2 ab = __ldg(reinterpret_cast<const double2*>(rp));
+                        const double sg = flip[u] ? -1.0 : 1.0;
+                        r[0] = ab.x; r[1 % (D * D)] = -sg * ab.y; r[2 % (D * D)] = ab.y; r[3 % (D * D)] = sg * ab.x;
+                    } else if ((D * D) % 2 == 0) {
 #pragma unroll
                         for (int v = 0; v < D * D; v += 2) {
                             const double2 rv = __ldg(reinterpret_cast<const double2*>(rp + v));
@@ -193,7 +207,7 @@ bsr_spmm_v2_kernel(int nbrows, const int* __restrict__ indptr, const int* __rest
     }
 }
 
-template <int D, bool PATTERN>
+template <int D, bool PATTERN, bool ROT2>
 static int launch_spmm_v2(Handle* h, int nbrows, const int* indptr, const int* indices, const double* vals,
                           const double* X, int64_t ldx, const double* W, int64_t ldw, double* Y, int64_t ldy,
                           int ncols, double alpha, double beta, double gamma) {
@@ -203,7 +217,7 @@ static int launch_spmm_v2(Handle* h, int nbrows, const int* indptr, const int* i
     do {                                                                                                   \
         constexpr int U = (D * CPL2 <= 2) ? 4 : ((D * CPL2 <= 4) ? 2 : 1);                                 \
         const int rows_per_cta = 8 * (32 / LPR) * rpg;                                                     \
-        bsr_spmm_v2_kernel<D, LPR, CPL2, U, PATTERN><<<cdiv(nbrows, rows_per_cta), 256, 0, h->stream>>>(   \
+        bsr_spmm_v2_kernel<D, LPR, CPL2, U, PATTERN, ROT2><<<cdiv(nbrows, rows_per_cta), 256, 0, h->stream>>>( \
             nbrows, indptr, indices, vals, X, ldx, W, ldw, Y, ldy, ncols, alpha, beta, gamma, rpg);        \
     } while (0)
     int lpr = h->spmm_lpr;
@@ -263,20 +277,25 @@ static int spmm_dispatch(Handle* h, int nbrows, int d, const int* indptr, const 
                          const double* X, int64_t ldx, const double* W, int64_t ldw, double* Y, int64_t ldy,
                          int ncols, double alpha, double beta, double gamma) {
     RVGP_REQUIRE(h, nbrows >= 0 && ncols >= 1 && ncols <= 64, "spmm: ncols must be in [1,64]");
+    RVGP_REQUIRE(h, d == -2 || d >= 1, "spmm: bad block size");
     RVGP_REQUIRE(h, gamma == 0.0 || W != nullptr, "spmm: W required when gamma != 0");
     RVGP_REQUIRE(h, Y != X && Y != W, "spmm: Y must not alias X or W");
     if (nbrows == 0) return RVGP_OK;
     const bool aligned = (ncols % 2 == 0) && (ldx % 2 == 0) && (ldy % 2 == 0) && (W == nullptr || ldw % 2 == 0) &&
                          ((uintptr_t)X % 16 == 0) && ((uintptr_t)Y % 16 == 0) && ((uintptr_t)W % 16 == 0) &&
                          (vals == nullptr || (uintptr_t)vals % 16 == 0) && !h->spmm_v1;
+    if (d == -2) {   // ROT2-compressed 2x2 blocks (see rvgp_bsr_compress_rot2)
+        RVGP_REQUIRE(h, aligned && vals != nullptr, "spmm: rot2 storage needs even ncols / leading dimensions and 16-byte aligned buffers");
+        return launch_spmm_v2<2, false, true>(h, nbrows, indptr, indices, vals, X, ldx, W, ldw, Y, ldy, ncols, alpha, beta, gamma);
+    }
     if (vals == nullptr) {
         RVGP_REQUIRE(h, d == 1, "spmm: pattern mode (vals == NULL) needs d == 1");
-        if (aligned) return launch_spmm_v2<1, true>(h, nbrows, indptr, indices, vals, X, ldx, W, ldw, Y, ldy, ncols, alpha, beta, gamma);
+        if (aligned) return launch_spmm_v2<1, true, false>(h, nbrows, indptr, indices, vals, X, ldx, W, ldw, Y, ldy, ncols, alpha, beta, gamma);
         return launch_spmm_d<1, true>(h, nbrows, indptr, indices, vals, X, ldx, W, ldw, Y, ldy, ncols, alpha, beta, gamma);
     }
     if (aligned) {
         switch (d) {
-#define RVGP_CASE(DD) case DD: return launch_spmm_v2<DD, false>(h, nbrows, indptr, indices, vals, X, ldx, W, ldw, Y, ldy, ncols, alpha, beta, gamma);
+#define RVGP_CASE(DD) case DD: return launch_spmm_v2<DD, false, false>(h, nbrows, indptr, indices, vals, X, ldx, W, ldw, Y, ldy, ncols, alpha, beta, gamma);
             RVGP_CASE(1) RVGP_CASE(2) RVGP_CASE(3) RVGP_CASE(4) RVGP_CASE(5) RVGP_CASE(6) RVGP_CASE(7) RVGP_CASE(8)
 #undef RVGP_CASE
             default: break;
@@ -299,6 +318,36 @@ extern "C" int rvgp_bsr_spmm_f64(rvgp_handle_t hh, int nbrows, int d, const int3
                                  double* Y, int64_t ldy, int ncols, double alpha, double beta, double gamma) {
     Handle* h = H(hh);
     return spmm_dispatch(h, nbrows, d, indptr, indices, vals, X, ldx, W, ldw, Y, ldy, ncols, alpha, beta, gamma);
+}
+
+namespace rvgp {
+__global__ void compress_rot2_kernel(int64_t nnzb, const double* __restrict__ vals, const int* __restrict__ indices,
+                                     double2* __restrict__ ab, int* __restrict__ idx_flag, int* __restrict__ bad, double rtol) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nnzb) return;
+    const double m00 = vals[4 * e], m01 = vals[4 * e + 1], m10 = vals[4 * e + 2], m11 = vals[4 * e + 3];
+    const double scale = fabs(m00) + fabs(m01) + fabs(m10) + fabs(m11);
+    // det sign decides rotation (s=+1: m11 = a, m01 = -b) or reflection (s=-1: m11 = -a, m01 = b)
+    const bool flip = (m00 * m11 - m01 * m10) < 0.0;
+    const double sg = flip ? -1.0 : 1.0;
+    if (fabs(m11 - sg * m00) > rtol * scale || fabs(m01 + sg * m10) > rtol * scale) atomicOr(bad, 1);
+    ab[e] = make_double2(m00, m10);
+    idx_flag[e] = indices[e] | (flip ? (int)0x80000000 : 0);
+}
+}  // namespace rvgp
+
+// Compress 2x2 blocks that are scaled orthogonal matrices to (a, b) + a flip bit in the column index (see ROT2 above).
+// bad_flag (device int32, zeroed here) gets bit0 set when some block is NOT of that form within rtol (then keep using
+// the plain storage).  Pass the outputs to rvgp_bsr_spmm_f64 / rvgp_cheb_filter_f64 with d = -2.
+extern "C" int rvgp_bsr_compress_rot2(rvgp_handle_t hh, int64_t nnzb, const double* vals, const int32_t* indices, double* ab,
+                                      int32_t* idx_flag, int32_t* bad_flag, double rtol) {
+    Handle* h = H(hh);
+    RVGP_CUDA_OK(h, cudaMemsetAsync(bad_flag, 0, sizeof(int), h->stream));
+    if (nnzb == 0) return RVGP_OK;
+    compress_rot2_kernel<<<cdiv(nnzb, 256), 256, 0, h->stream>>>(nnzb, vals, indices, reinterpret_cast<double2*>(ab), idx_flag,
+                                                                  bad_flag, rtol);
+    RVGP_LAUNCH_OK(h, "compress_rot2_kernel");
+    return RVGP_OK;
 }
 
 namespace rvgp {
@@ -349,11 +398,11 @@ extern "C" int rvgp_cheb_filter_f64(rvgp_handle_t hh, int nbrows, int d, const i
     int slot = 0;
     auto apply = [&](const double* X, int64_t ldx, const double* W, int64_t ldw_, double* Y, int64_t ldy, double a, double b,
                      double g) { return spmm_dispatch(h, nbrows, d, indptr, indices, vals, X, ldx, W, ldw_, Y, ldy, ncols, a, b, g); };
-    int rc = cheb_recurrence(h, apply, (int64_t)nbrows * d, buf, ld, ncols, degree, lo_spec, lo_cut, hi, &slot);
+    int rc = cheb_recurrence(h, apply, (int64_t)nbrows * (d < 0 ? -d : d), buf, ld, ncols, degree, lo_spec, lo_cut, hi, &slot);
     if (rc) return rc;
     if (slot != 0) {
         RVGP_CUDA_OK(h, cudaMemcpy2DAsync(V, ldv * sizeof(double), buf[slot], ld[slot] * sizeof(double),
-                                          (size_t)ncols * sizeof(double), (size_t)nbrows * d,
+                                          (size_t)ncols * sizeof(double), (size_t)nbrows * (d < 0 ? -d : d),
                                           cudaMemcpyDeviceToDevice, h->stream));
     }
     return RVGP_OK;

@@ -28,6 +28,23 @@ class BsrMatrix:
         self.nrows = self.nbrows * self.d
         self.nnzb = int(indices.numel())
         self.max_offdiag = max_offdiag   # max number of off-diagonal blocks in a row (Gershgorin)
+        self.d_code, self.indices_k, self.vals_k = self.d, indices, vals     # what the kernels are given
+
+    def compress_rot2(self, rtol=1e-12, h=None):
+        """Switch the kernels to ROT2 storage (d == 2, every block a scaled 2x2 orthogonal matrix).  Returns True on
+        success; the plain arrays stay available for everything else."""
+        if self.d != 2 or self.vals is None or self.nnzb == 0:
+            return False
+        h = h or get_handle(self.indptr.device.index)
+        dev = self.indptr.device
+        ab = torch.empty((self.nnzb, 2), dtype=torch.float64, device=dev)
+        idxf = torch.empty(self.nnzb, dtype=torch.int32, device=dev)
+        bad = torch.zeros(1, dtype=torch.int32, device=dev)
+        h.call("rvgp_bsr_compress_rot2", I64(self.nnzb), self.vals, self.indices, ab, idxf, bad, float(rtol))
+        if int(bad.item()) != 0:
+            return False
+        self.d_code, self.indices_k, self.vals_k = -2, idxf, ab
+        return True
 
     def spmm_bytes(self, ncols, fused=False):
         """Algorithmic HBM bytes of one SpMM launch (SURVEY.md 8d / DESIGN.md K9)."""
@@ -38,7 +55,13 @@ class BsrMatrix:
     def spmm(self, X, Y, alpha=1.0, beta=0.0, gamma=0.0, W=None, h=None):
         h = h or get_handle(X.device.index)
         ncols = X.shape[1]
-        h.call("rvgp_bsr_spmm_f64", self.nbrows, self.d, self.indptr, self.indices, self.vals,
+        aligned = (ncols % 2 == 0 and X.stride(0) % 2 == 0 and Y.stride(0) % 2 == 0 and X.data_ptr() % 16 == 0
+                   and Y.data_ptr() % 16 == 0 and (W is None or (W.stride(0) % 2 == 0 and W.data_ptr() % 16 == 0)))
+        if self.d_code == -2 and aligned:
+            dc, ix, vl = self.d_code, self.indices_k, self.vals_k
+        else:
+            dc, ix, vl = self.d, self.indices, self.vals
+        h.call("rvgp_bsr_spmm_f64", self.nbrows, dc, self.indptr, ix, vl,
                X, I64(X.stride(0)), W, I64(W.stride(0) if W is not None else 0), Y, I64(Y.stride(0)),
                int(ncols), float(alpha), float(beta), float(gamma))
         return Y
@@ -99,7 +122,13 @@ class BsrMatrix:
     def cheb_filter(self, Vp, w0, w1, ncols, degree, lo_spec, lo_cut, hi, h=None):
         """Degree-`degree` Chebyshev filter of the panel Vp in place; the whole recurrence runs inside one C call."""
         h = h or get_handle(Vp.device.index)
-        h.call("rvgp_cheb_filter_f64", self.nbrows, self.d, self.indptr, self.indices, self.vals, Vp, I64(Vp.stride(0)),
+        aligned = (ncols % 2 == 0 and Vp.stride(0) % 2 == 0 and w0.stride(0) % 2 == 0 and Vp.data_ptr() % 16 == 0
+                   and w0.data_ptr() % 16 == 0 and w1.data_ptr() % 16 == 0)
+        if self.d_code == -2 and aligned:
+            dc, ix, vl = self.d_code, self.indices_k, self.vals_k
+        else:
+            dc, ix, vl = self.d, self.indices, self.vals
+        h.call("rvgp_cheb_filter_f64", self.nbrows, dc, self.indptr, ix, vl, Vp, I64(Vp.stride(0)),
                w0, w1, I64(w0.stride(0)), int(ncols), int(degree), float(lo_spec), float(lo_cut), float(hi))
 
     def matmat(self, X, out=None, h=None):
@@ -166,7 +195,8 @@ class _Dense:
 
 
 def smallest_eigenpairs(A, k, upper_bound, lower_bound=0.0, tol=1e-12, nex=None, seed=0, max_outer=80,
-                        cond_max=1e6, deg0=20, panel=None, stats=None, verbose=False, comm=None):
+                        cond_max=1e6, deg0=20, panel=None, stats=None, verbose=False, comm=None,
+                        refine_bound=True):
     """Smallest k eigenpairs of the symmetric PSD BsrMatrix ``A``.
 
     upper_bound: a rigorous upper bound of the spectrum (2 * max degree for (connection) Laplacians).
@@ -192,11 +222,17 @@ def smallest_eigenpairs(A, k, upper_bound, lower_bound=0.0, tol=1e-12, nex=None,
     if m < Nglob:
         m = min(Nglob, ((m + panel - 1) // panel) * panel)
     hi = float(upper_bound)
+    if refine_bound and Nglob > 4 * m:
+        # Gershgorin (2 * max degree) overestimates lambda_max of kNN-graph Laplacians by ~1.5x; the filter degree scales
+        # with sqrt(hi), so a 24-step Lanczos bound pays for itself many times over
+        hi = min(hi, 1.01 * lanczos_upper_bound(A, comm=comm, h=h))
     lo_spec = float(lower_bound)
-    tol_abs = tol * hi
+    tol_abs = tol * float(upper_bound)
     st = stats if stats is not None else {}
     st.update(dict(N=N, k=k, m=m, panel=panel, spmm_launches=0, filter_launches=0, filter_col_degrees=0, outer=0,
-                   t_filter=0.0, t_dense=0.0, t_host=0.0))
+                   t_filter=0.0, t_dense=0.0, t_host=0.0, spmm_bytes_fused=int(A.spmm_bytes(panel, fused=True)),
+                   spmm_bytes_plain=int(A.spmm_bytes(panel, fused=False)), d=A.d, world=(comm.world if comm else 1),
+                   hi=hi, hi_gershgorin=float(upper_bound)))
 
     B1 = torch.empty((N, m), dtype=torch.float64, device=dev)
     B2 = torch.empty((N, m), dtype=torch.float64, device=dev)
@@ -294,6 +330,39 @@ def smallest_eigenpairs(A, k, upper_bound, lower_bound=0.0, tol=1e-12, nex=None,
     evals = theta_d[:k].clone()
     evecs = V[:, :k].contiguous()     # copy out so the (N x m) work buffers can be freed
     return evals, evecs
+
+
+def lanczos_upper_bound(A, steps=24, seed=12345, comm=None, h=None):
+    """Safeguarded upper bound of the spectrum of the symmetric operator A from a `steps`-step Lanczos run
+    (Zhou & Li 2011: theta_max + |beta_k|).  One single-column SpMM, two dot products and two axpys per step."""
+    dev = A.indptr.device
+    h = h or get_handle(dev.index)
+    N = A.nrows
+    dense = _Dense(h, N, 1, dev, comm)
+    v = torch.empty((N, 1), dtype=torch.float64, device=dev)
+    vp = torch.zeros((N, 1), dtype=torch.float64, device=dev)
+    w = torch.empty((N, 1), dtype=torch.float64, device=dev)
+    h.call("rvgp_fill_uniform_f64", I64(N), 1, v, I64(1), U64(seed), I64(0), I64(A.row_offset))
+    nrm = math.sqrt(float(dense.coldot(v, v).item()))
+    dense.colscale(v, torch.full((1,), 1.0 / nrm, dtype=torch.float64, device=dev))
+    alphas, betas = [], []
+    beta = 0.0
+    for j in range(steps):
+        A.matmat(v, out=w, h=h)
+        alpha = float(dense.coldot(w, v).item())
+        h.call("rvgp_axpy_f64", I64(N), 1, -alpha, v, I64(1), w, I64(1))
+        if j > 0:
+            h.call("rvgp_axpy_f64", I64(N), 1, -beta, vp, I64(1), w, I64(1))
+        beta = math.sqrt(max(float(dense.coldot(w, w).item()), 0.0))
+        alphas.append(alpha)
+        betas.append(beta)
+        if beta < 1e-14 * max(1.0, abs(alpha)):
+            break
+        vp, v, w = v, w, vp
+        dense.colscale(v, torch.full((1,), 1.0 / beta, dtype=torch.float64, device=dev))
+    T = np.diag(alphas) + np.diag(betas[:-1], 1) + np.diag(betas[:-1], -1)
+    theta = np.linalg.eigvalsh(T)
+    return float(theta[-1] + abs(betas[-1]))
 
 
 def _chol_upper_shifted(G):

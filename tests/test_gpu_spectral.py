@@ -81,12 +81,14 @@ def test_cheb_filter_matches_recurrence(degree):
     assert np.abs(V.cpu().numpy() - Y).max() <= 1e-12 * np.abs(Y).max()
 
 
+@pytest.mark.parametrize("dmma", [0, 1])
 @pytest.mark.parametrize("shape", [(1, 1, 5), (37, 53, 1000), (200, 129, 4097), (256, 256, 70000), (130, 7, 333)])
-def test_dgemm_layouts(shape):
+def test_dgemm_layouts(shape, dmma):
     from rvgp_b200.eigensolver import _dgemm
     from rvgp_b200._cabi import get_handle
     m, n, k = shape
     h = get_handle(0)
+    h.set_option("dgemm_dmma", dmma)
     rng = np.random.default_rng(0)
     for akm in (0, 1):
         for bkm in (0, 1):
@@ -103,6 +105,7 @@ def test_dgemm_layouts(shape):
                 err = np.abs(C[:, :n].cpu().numpy() - ref).max()
                 assert err <= 1e-13 * k ** 0.5 * max(1, np.abs(ref).max()), (akm, bkm, split, err)
                 assert C[:, n:].abs().max().item() == 0.0
+    h.set_option("dgemm_dmma", 0)
 
 
 def test_column_reductions_and_utils():
@@ -200,3 +203,23 @@ def test_spmm_tiled_rejects_unaligned():
     X = torch.zeros((A.nrows, 7), dtype=torch.float64, device=_dev())
     with pytest.raises(ValueError):
         A.spmm_tiled(plan, X, torch.empty_like(X))
+
+
+@pytest.mark.parametrize("ncols", [2, 16, 32, 64])
+def test_spmm_rot2_storage(ncols):
+    """ROT2 (a, b, flip) storage of the 2x2 connection blocks gives the same product as the plain blocks."""
+    g = load_golden("sphere_n2000_k50")
+    A, S = _bsr_from_golden(g, "Lc")
+    assert A.compress_rot2() and A.d_code == -2
+    rng = np.random.default_rng(4)
+    X = rng.normal(size=(A.nrows, ncols)); W = rng.normal(size=(A.nrows, ncols))
+    Xd, Wd = torch.from_numpy(X).to(_dev()), torch.from_numpy(W).to(_dev())
+    Yd = torch.empty_like(Xd)
+    A.spmm(Xd, Yd, alpha=0.7, beta=-1.3, gamma=0.25, W=Wd)
+    ref = 0.7 * (S @ X) - 1.3 * X + 0.25 * W
+    assert np.abs(Yd.cpu().numpy() - ref).max() <= 1e-13 * np.abs(ref).max()
+    # a matrix whose blocks are NOT scaled rotations / reflections is refused
+    from rvgp_b200.eigensolver import BsrMatrix
+    vals = torch.from_numpy(g["Lc_data"].copy()); vals[5, 0, 1] += 0.3
+    B = BsrMatrix(A.nbrows, 2, A.indptr, A.indices, vals.to(_dev()))
+    assert not B.compress_rot2() and B.d_code == 2

@@ -173,7 +173,7 @@ def run_b200(args):
             traffic = json.load(open(tp)).get(wl)
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "bsr_spmm_kernel (fused Chebyshev step, d=%d, %d columns)" % (A.d, panel),
+    roofline = {"bound": "hbm", "kernel": "bsr_spmm_v2_kernel (fused Chebyshev step, d=%d, %d columns)" % (A.d, panel),
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "traffic": traffic, "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback",
                 "algorithmic_bytes_per_launch": int(bytes_fused), "avg_launch_ms": round(t_launch * 1e3, 4),

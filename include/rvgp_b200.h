@@ -88,6 +88,23 @@ int rvgp_cheb_filter_tiled_f64(rvgp_handle_t h, int nbrows, int d, int TR, int u
                                const double* vals, double* V, int64_t ldv, double* work0, double* work1, double* work2,
                                int ncols, int degree, double lo_spec, double lo_cut, double hi);
 
+/* ---- K9 v3: row-group merged SpMM.  R (4 or 8) consecutive block rows are processed together over the UNION of
+ * their column lists (uent: int32 pairs (column, R-bit row mask); gptr: ngroups+1 offsets), so one gather of a
+ * neighbour's X rows serves every row that stores it.  rvgp_bsr_merge_plan is called twice: first with uent == NULL
+ * (fills gptr; gptr[ngroups] = number of union entries), then with uent allocated.  Same contract / alignment needs
+ * as the 128-bit path of rvgp_bsr_spmm_f64; d = -2 selects ROT2 storage. */
+int rvgp_bsr_merge_plan(rvgp_handle_t h, int nbrows, const int32_t* indptr, const int32_t* indices, int R,
+                        int32_t* gptr, int32_t* uent, void* workspace, int64_t workspace_bytes);
+int64_t rvgp_bsr_merge_plan_workspace_bytes(int nbrows, int R);
+int rvgp_bsr_spmm_merged_f64(rvgp_handle_t h, int nbrows, int d, int R, const int32_t* indptr, const int32_t* indices,
+                             const int32_t* gptr, const int32_t* uent, const double* vals, const double* X, int64_t ldx,
+                             const double* W, int64_t ldw, double* Y, int64_t ldy, int ncols, double alpha, double beta,
+                             double gamma);
+int rvgp_cheb_filter_merged_f64(rvgp_handle_t h, int nbrows, int d, int R, const int32_t* indptr, const int32_t* indices,
+                                const int32_t* gptr, const int32_t* uent, const double* vals, double* V, int64_t ldv,
+                                double* work0, double* work1, int64_t ldw, int ncols, int degree, double lo_spec,
+                                double lo_cut, double hi);
+
 /* ---- K10: dense FP64 kernels for orthogonalisation / Rayleigh-Ritz ---------------------------------
  * C (m x n, ldc) = alpha * op(A) * op(B).  Layout flags say which index of each operand is contiguous:
  *   a_kmajor = 0: A(i,k) = A[k*lda + i]  ("A is stored as K x M", e.g. V^T of a tall block vector)
@@ -101,6 +118,10 @@ int rvgp_dgemm_f64(rvgp_handle_t h, int m, int n, int64_t k, double alpha, const
                    int a_kmajor, const double* B, int64_t ldb, int b_kmajor, const double* scale_k,
                    double* C, int64_t ldc, int split_k, double* workspace);
 int64_t rvgp_dgemm_workspace_bytes(int m, int n, int split_k);
+/* symmetric results (Gram matrices): only tiles intersecting the lower triangle are computed; upper part undefined */
+int rvgp_dgemm_lower_f64(rvgp_handle_t h, int m, int n, int64_t k, double alpha, const double* A, int64_t lda,
+                         int a_kmajor, const double* B, int64_t ldb, int b_kmajor, double* C, int64_t ldc, int split_k,
+                         double* workspace);
 
 /* column-wise reductions over tall block vectors (deterministic two-stage) ---------------------------
  * out[c] = sum_r A[r*lda+c] * B[r*ldb+c]   (B == NULL: B = 1, i.e. column sums).

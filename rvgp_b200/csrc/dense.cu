@@ -388,6 +388,14 @@ extern "C" int rvgp_dgemm_f64(rvgp_handle_t hh, int m, int n, int64_t k, double 
                         workspace, 0);
 }
 
+// Same as rvgp_dgemm_f64 but only the tiles that intersect the LOWER triangle of C are computed (C symmetric by
+// construction: Gram matrices V^T V, V^T A V); the strict upper triangle of C is left untouched / undefined.
+extern "C" int rvgp_dgemm_lower_f64(rvgp_handle_t hh, int m, int n, int64_t k, double alpha, const double* A, int64_t lda,
+                                    int a_kmajor, const double* B, int64_t ldb, int b_kmajor, double* C, int64_t ldc,
+                                    int split_k, double* workspace) {
+    return dgemm_launch(H(hh), m, n, k, alpha, A, lda, a_kmajor, B, ldb, b_kmajor, nullptr, 0.0, C, ldc, split_k, workspace, 1);
+}
+
 // C = alpha * op(A) op(B) + beta * C   (same layout flags as rvgp_dgemm_f64; no split-K)
 extern "C" int rvgp_dgemm_acc_f64(rvgp_handle_t hh, int m, int n, int64_t k, double alpha, const double* A, int64_t lda,
                                   int a_kmajor, const double* B, int64_t ldb, int b_kmajor, double beta, double* C,

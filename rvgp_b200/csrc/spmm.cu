@@ -232,7 +232,7 @@ static int launch_spmm_v2(Handle* h, int nbrows, const int* indptr, const int* i
     const int cpl = (npairs + lpr - 1) / lpr;
     if (lpr == 8) { if (cpl <= 1) RVGP_V2(8, 1); else if (cpl <= 2) RVGP_V2(8, 2); else RVGP_V2(8, 4); }
     else if (lpr == 16) { if (cpl <= 1) RVGP_V2(16, 1); else RVGP_V2(16, 2); }
-    else RVGP_V2(32, 1);
+    else { if (cpl <= 1) RVGP_V2(32, 1); else RVGP_V2(32, 2); }
 #undef RVGP_V2
     RVGP_LAUNCH_OK(h, "bsr_spmm_v2_kernel");
     return RVGP_OK;
@@ -276,14 +276,16 @@ static int launch_spmm_d(Handle* h, int nbrows, const int* indptr, const int* in
 static int spmm_dispatch(Handle* h, int nbrows, int d, const int* indptr, const int* indices, const double* vals,
                          const double* X, int64_t ldx, const double* W, int64_t ldw, double* Y, int64_t ldy,
                          int ncols, double alpha, double beta, double gamma) {
-    RVGP_REQUIRE(h, nbrows >= 0 && ncols >= 1 && ncols <= 64, "spmm: ncols must be in [1,64]");
+    RVGP_REQUIRE(h, nbrows >= 0 && ncols >= 1 && ncols <= 128, "spmm: ncols must be in [1,128]");
     RVGP_REQUIRE(h, d == -2 || d >= 1, "spmm: bad block size");
     RVGP_REQUIRE(h, gamma == 0.0 || W != nullptr, "spmm: W required when gamma != 0");
     RVGP_REQUIRE(h, Y != X && Y != W, "spmm: Y must not alias X or W");
     if (nbrows == 0) return RVGP_OK;
-    const bool aligned = (ncols % 2 == 0) && (ldx % 2 == 0) && (ldy % 2 == 0) && (W == nullptr || ldw % 2 == 0) &&
+    const bool aligned0 = (ncols % 2 == 0) && (ldx % 2 == 0) && (ldy % 2 == 0) && (W == nullptr || ldw % 2 == 0) &&
                          ((uintptr_t)X % 16 == 0) && ((uintptr_t)Y % 16 == 0) && ((uintptr_t)W % 16 == 0) &&
-                         (vals == nullptr || (uintptr_t)vals % 16 == 0) && !h->spmm_v1;
+                         (vals == nullptr || (uintptr_t)vals % 16 == 0);
+    RVGP_REQUIRE(h, ncols <= 64 || aligned0, "spmm: more than 64 columns needs the 128-bit path (even ncols / ld, 16-byte alignment)");
+    const bool aligned = aligned0 && (!h->spmm_v1 || ncols > 64);
     if (d == -2) {   // ROT2-compressed 2x2 blocks (see rvgp_bsr_compress_rot2)
         RVGP_REQUIRE(h, aligned && vals != nullptr, "spmm: rot2 storage needs even ncols / leading dimensions and 16-byte aligned buffers");
         return launch_spmm_v2<2, false, true>(h, nbrows, indptr, indices, vals, X, ldx, W, ldw, Y, ldy, ncols, alpha, beta, gamma);
@@ -404,6 +406,39 @@ extern "C" int rvgp_cheb_filter_f64(rvgp_handle_t hh, int nbrows, int d, const i
         RVGP_CUDA_OK(h, cudaMemcpy2DAsync(V, ldv * sizeof(double), buf[slot], ld[slot] * sizeof(double),
                                           (size_t)ncols * sizeof(double), (size_t)nbrows * (d < 0 ? -d : d),
                                           cudaMemcpyDeviceToDevice, h->stream));
+    }
+    return RVGP_OK;
+}
+
+namespace rvgp {
+int spmm_merged_dispatch(Handle* h, int nbrows, int d, int R, const int* indptr, const int* indices, const int* gptr,
+                         const int* uent, const double* vals, const double* X, int64_t ldx, const double* W, int64_t ldw,
+                         double* Y, int64_t ldy, int ncols, double alpha, double beta, double gamma);
+}
+
+// Same filter through the row-group merged SpMM (rvgp_bsr_spmm_merged_f64, spmm_merged.cu).
+extern "C" int rvgp_cheb_filter_merged_f64(rvgp_handle_t hh, int nbrows, int d, int R, const int32_t* indptr,
+                                           const int32_t* indices, const int32_t* gptr, const int32_t* uent,
+                                           const double* vals, double* V, int64_t ldv, double* work0, double* work1,
+                                           int64_t ldw, int ncols, int degree, double lo_spec, double lo_cut, double hi) {
+    Handle* h = H(hh);
+    RVGP_REQUIRE(h, degree >= 0, "cheb_filter: degree >= 0");
+    RVGP_REQUIRE(h, hi > lo_cut && lo_cut > lo_spec, "cheb_filter: need lo_spec < lo_cut < hi");
+    if (degree == 0 || nbrows == 0) return RVGP_OK;
+    const int dd = d < 0 ? -d : d;
+    double* buf[3] = {V, work0, work1};
+    int64_t ld[3] = {ldv, ldw, ldw};
+    int slot = 0;
+    auto apply = [&](const double* X, int64_t ldx, const double* W, int64_t ldw_, double* Y, int64_t ldy, double a, double b,
+                     double g) {
+        return spmm_merged_dispatch(h, nbrows, d, R, indptr, indices, gptr, uent, vals, X, ldx, W, ldw_, Y, ldy, ncols, a, b, g);
+    };
+    int rc = cheb_recurrence(h, apply, (int64_t)nbrows * dd, buf, ld, ncols, degree, lo_spec, lo_cut, hi, &slot);
+    if (rc) return rc;
+    if (slot != 0) {
+        RVGP_CUDA_OK(h, cudaMemcpy2DAsync(V, ldv * sizeof(double), buf[slot], ld[slot] * sizeof(double),
+                                          (size_t)ncols * sizeof(double), (size_t)nbrows * dd, cudaMemcpyDeviceToDevice,
+                                          h->stream));
     }
     return RVGP_OK;
 }

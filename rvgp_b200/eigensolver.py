@@ -61,10 +61,45 @@ class BsrMatrix:
             dc, ix, vl = self.d_code, self.indices_k, self.vals_k
         else:
             dc, ix, vl = self.d, self.indices, self.vals
+        if self._merged_ok(ncols, X, Y, W):
+            mp = self.merged
+            h.call("rvgp_bsr_spmm_merged_f64", self.nbrows, dc, mp["R"], self.indptr, ix, mp["gptr"], mp["uent"], vl,
+                   X, I64(X.stride(0)), W, I64(W.stride(0) if W is not None else 0), Y, I64(Y.stride(0)),
+                   int(ncols), float(alpha), float(beta), float(gamma))
+            return Y
         h.call("rvgp_bsr_spmm_f64", self.nbrows, dc, self.indptr, ix, vl,
                X, I64(X.stride(0)), W, I64(W.stride(0) if W is not None else 0), Y, I64(Y.stride(0)),
                int(ncols), float(alpha), float(beta), float(gamma))
         return Y
+
+    # ---- row-group merged variant (K9 v3) -------------------------------------------------------------------
+    def build_merge_plan(self, R=4, h=None):
+        """Union column lists of groups of R consecutive block rows (rvgp_bsr_merge_plan)."""
+        plans = self.__dict__.setdefault("_mplans", {})
+        if R in plans:
+            return plans[R]
+        h = h or get_handle(self.indptr.device.index)
+        dev = self.indptr.device
+        ngroups = (self.nbrows + R - 1) // R
+        wsb = h.query("rvgp_bsr_merge_plan_workspace_bytes", int(self.nbrows), int(R))
+        ws = torch.empty(max(8, wsb), dtype=torch.uint8, device=dev)
+        gptr = torch.empty(ngroups + 1, dtype=torch.int32, device=dev)
+        h.call("rvgp_bsr_merge_plan", self.nbrows, self.indptr, self.indices, int(R), gptr, None, ws, I64(wsb))
+        total = int(gptr[-1].item())
+        uent = torch.empty((max(1, total), 2), dtype=torch.int32, device=dev)
+        h.call("rvgp_bsr_merge_plan", self.nbrows, self.indptr, self.indices, int(R), gptr, uent, ws, I64(wsb))
+        plans[R] = dict(R=int(R), gptr=gptr, uent=uent, total=total, reuse=self.nnzb / max(1, total))
+        return plans[R]
+
+    def enable_merged(self, R=4, h=None):
+        """Route spmm / cheb_filter through the merged kernel when the buffers allow it."""
+        self.merged = self.build_merge_plan(R, h=h)
+        return self.merged
+
+    def _merged_ok(self, ncols, *tensors):
+        if getattr(self, "merged", None) is None or ncols % 2 or self.d > 3:
+            return False
+        return all(t is None or (t.stride(0) % 2 == 0 and t.data_ptr() % 16 == 0) for t in tensors)
 
     # ---- shared-memory-staged variant (K9 v2) ---------------------------------------------------------
     def build_plan(self, TR, ucap=None, h=None):
@@ -128,6 +163,12 @@ class BsrMatrix:
             dc, ix, vl = self.d_code, self.indices_k, self.vals_k
         else:
             dc, ix, vl = self.d, self.indices, self.vals
+        if self._merged_ok(ncols, Vp, w0, w1):
+            mp = self.merged
+            h.call("rvgp_cheb_filter_merged_f64", self.nbrows, dc, mp["R"], self.indptr, ix, mp["gptr"], mp["uent"], vl,
+                   Vp, I64(Vp.stride(0)), w0, w1, I64(w0.stride(0)), int(ncols), int(degree), float(lo_spec),
+                   float(lo_cut), float(hi))
+            return
         h.call("rvgp_cheb_filter_f64", self.nbrows, dc, self.indptr, ix, vl, Vp, I64(Vp.stride(0)),
                w0, w1, I64(w0.stride(0)), int(ncols), int(degree), float(lo_spec), float(lo_cut), float(hi))
 
@@ -159,14 +200,24 @@ class _Dense:
         self.red_ws = torch.empty(max(1, nred), dtype=torch.float64, device=device)
         self.small = torch.empty(m, dtype=torch.float64, device=device)
 
-    def gram(self, V, W, out):
-        """out (m1 x m2) = V^T W."""
+    def gram(self, V, W, out, sym=False):
+        """out (m1 x m2) = V^T W.  sym=True: the result is symmetric, only its lower-triangle tiles are computed
+        (read it back with ``sym_to_host``)."""
         m1, m2 = V.shape[1], W.shape[1]
-        _dgemm(self.h, m1, m2, self.N, V, V.stride(0), 0, W, W.stride(0), 0, out, out.stride(0),
-               split_k=self.split, ws=self.ws)
+        if sym:
+            self.h.call("rvgp_dgemm_lower_f64", int(m1), int(m2), I64(self.N), 1.0, V, I64(V.stride(0)), 0, W,
+                        I64(W.stride(0)), 0, out, I64(out.stride(0)), int(self.split), self.ws)
+        else:
+            _dgemm(self.h, m1, m2, self.N, V, V.stride(0), 0, W, W.stride(0), 0, out, out.stride(0),
+                   split_k=self.split, ws=self.ws)
         if self.comm is not None:
             self.comm.allreduce_(out)            # row-sharded: sum of the ranks' partial Gram matrices
         return out
+
+    @staticmethod
+    def sym_to_host(Gd):
+        G = np.tril(Gd.cpu().numpy())
+        return G + np.tril(G, -1).T
 
     def apply(self, V, Cm, out):
         """out (N x m2) = V (N x m1) @ Cm (m1 x m2)."""
@@ -275,10 +326,10 @@ def smallest_eigenpairs(A, k, upper_bound, lower_bound=0.0, tol=1e-12, nex=None,
             nrm = dense.coldot(V, V)
             inv = torch.rsqrt(nrm)
             dense.colscale(V, inv)
-            dense.gram(V, V, Gd)
-            G = Gd.cpu().numpy()
+            Gd.zero_()
+            dense.gram(V, V, Gd, sym=True)
+            G = dense.sym_to_host(Gd)
             t0 = time.perf_counter()
-            G = 0.5 * (G + G.T)
             R, shifted = _chol_upper_shifted(G)
             Rinv = _tri_inv_upper(R)
             st["t_host"] += time.perf_counter() - t0
@@ -290,10 +341,11 @@ def smallest_eigenpairs(A, k, upper_bound, lower_bound=0.0, tol=1e-12, nex=None,
                 break
         A.matmat(V, out=W, h=h)                            # W = A V
         st["spmm_launches"] += math.ceil(m / 64)
-        dense.gram(V, V, Gd)
-        dense.gram(V, W, Hd)
-        G = Gd.cpu().numpy(); G = 0.5 * (G + G.T)
-        Hm = Hd.cpu().numpy(); Hm = 0.5 * (Hm + Hm.T)
+        Gd.zero_(); Hd.zero_()
+        dense.gram(V, V, Gd, sym=True)
+        dense.gram(V, W, Hd, sym=True)               # V^T A V is symmetric
+        G = dense.sym_to_host(Gd)
+        Hm = dense.sym_to_host(Hd)
         t0 = time.perf_counter()
         R2 = np.linalg.cholesky(G).T
         R2inv = _tri_inv_upper(R2)

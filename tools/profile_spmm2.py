@@ -13,13 +13,13 @@ def main():
     h = get_handle(0)
     out = {}
     for name, M in (("Lc", A), ("L", L)):
-        for b in (16, 32, 64):
+        for b in (64, 128):
             X = torch.randn((M.nrows, b), dtype=torch.float64, device=dev)
             W = torch.randn((M.nrows, b), dtype=torch.float64, device=dev)
             Y = torch.empty_like(X); Yref = torch.empty_like(X)
             kw = dict(alpha=0.7, beta=-0.2, gamma=0.1, W=W)
-            h.set_option("spmm_v1", 1); h.set_option("spmm_lpr", 32); M.spmm(X, Yref, **kw)
-            for code in (8, 16, 32, 108, 116, 132):
+            h.set_option("spmm_v1", 0); h.set_option("spmm_lpr", 32); M.spmm(X, Yref, **kw)
+            for code in (16, 32):
                 v1 = 1 if code > 100 else 0
                 lpr = code % 100
                 h.set_option("spmm_v1", v1)

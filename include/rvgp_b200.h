@@ -225,6 +225,15 @@ int rvgp_add_diag_f64(rvgp_handle_t h, double* A, int64_t lda, int n, double v);
 int rvgp_logdiag_sum_f64(rvgp_handle_t h, const double* A, int64_t lda, int n, double* out);
 int rvgp_kdiag_f64(rvgp_handle_t h, const double* X, int64_t ldx, int64_t n, int k, const double* S, double* out);
 
+/* ---- K16: fused rank-k GP evaluation for small k (<= 64), one CTA per problem (many time frames per launch; the
+ * EEG-shaped workload of examples/eeg_example/eeg_utils.py:26-35,107-112).  Inputs per problem: G = Phi^T Phi (k x k),
+ * b = Phi^T y, yy = y^T y, Mrows, spectral density s (k), noise.  Strides (in doubles) of 0 share an array between
+ * problems.  out per problem: [lml, dLML/dnoise, dLML/dS (k), posterior mean weights (k), Q = L_b^-1 S^1/2 (k*k)
+ * when want_predict].  lml is NaN when B is not positive definite. */
+int rvgp_gp_lowrank_small_f64(rvgp_handle_t h, int nprob, int k, const double* G, int64_t g_stride, const double* b,
+                              int64_t b_stride, const double* yy, const double* Mrows, const double* s, int64_t s_stride,
+                              const double* noise, double* out, int64_t out_stride, int want_predict);
+
 #ifdef __cplusplus
 }
 #endif

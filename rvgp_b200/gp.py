@@ -85,6 +85,26 @@ class DeviceGPR:
         Gh = Gd.cpu().numpy()
         Gh = 0.5 * (Gh + Gh.T)
         self.G, self.b, self.yy = Gh[:k, :k].copy(), Gh[:k, k].copy(), float(Gh[k, k])
+        self._small = k <= 64
+        if self._small:
+            # K16: everything an evaluation needs stays resident; one fused launch per evaluation
+            self._Gd = _f64(self.G, self.dev)
+            self._bd = _f64(self.b, self.dev)
+            self._scal = _f64(np.array([self.yy, float(M)]), self.dev)
+            self._par_h = torch.empty(k + 1, dtype=torch.float64).pin_memory()
+            self._par_d = torch.empty(k + 1, dtype=torch.float64, device=self.dev)
+            self._out_d = torch.empty(2 + 2 * k + k * k, dtype=torch.float64, device=self.dev)
+
+    def _small_eval(self, S, noise, want_predict):
+        k = self.k
+        self._par_h[:k] = torch.from_numpy(np.ascontiguousarray(S))
+        self._par_h[k] = noise
+        self._par_d.copy_(self._par_h, non_blocking=True)
+        self.h.sync_stream()
+        self.h.call("rvgp_gp_lowrank_small_f64", 1, int(k), self._Gd, I64(0), self._bd, I64(0), self._scal[0:1],
+                    self._scal[1:2], self._par_d, I64(0), self._par_d[k:k + 1], self._out_d, I64(self._out_d.numel()),
+                    int(want_predict))
+        return self._out_d.cpu().numpy()
 
     # ---- log marginal likelihood and gradient ------------------------------------------------------------
     def lml_and_grads(self, S, noise, grads=True):
@@ -103,6 +123,11 @@ class DeviceGPR:
 
     def _lml_lowrank(self, S, noise, grads):
         k, M = self.k, self.M
+        if getattr(self, "_small", False):
+            o = self._small_eval(S, noise, False)
+            if not np.isfinite(o[0]):
+                raise RvgpError(RVGP_ERR_NOT_SPD, "Cholesky decomposition was not successful. The input might not be valid.")
+            return (float(o[0]), o[2:2 + k].copy(), float(o[1])) if grads else float(o[0])
         rs, ch = self._lowrank_factor(S, noise)
         bt = rs * self.b
         rhs = _f64(bt.reshape(k, 1), self.dev)
@@ -181,13 +206,20 @@ class DeviceGPR:
         var = torch.empty((Ns, 1), dtype=torch.float64, device=self.dev)
         h, k = self.h, self.k
         if self.solver == "lowrank":
-            rs, ch = self._lowrank_factor(S, noise)
-            rhs = _f64((rs * self.b).reshape(k, 1), self.dev)
-            ch.solve(rhs, 0); ch.solve(rhs, 1)
-            wbar = _f64((rs * rhs.cpu().numpy()[:, 0] / noise).reshape(k, 1), self.dev)
-            Q = _f64(np.diag(rs), self.dev)
-            ch.solve(Q, 0)                               # L_b^-1 S^1/2
-            ch.check()
+            if getattr(self, "_small", False):
+                o = self._small_eval(S, noise, True)
+                if not np.isfinite(o[0]):
+                    raise RvgpError(RVGP_ERR_NOT_SPD, "Cholesky decomposition was not successful.")
+                wbar = self._out_d[2 + k:2 + 2 * k].reshape(k, 1).clone()
+                Q = self._out_d[2 + 2 * k:2 + 2 * k + k * k].reshape(k, k).clone()
+            else:
+                rs, ch = self._lowrank_factor(S, noise)
+                rhs = _f64((rs * self.b).reshape(k, 1), self.dev)
+                ch.solve(rhs, 0); ch.solve(rhs, 1)
+                wbar = _f64((rs * rhs.cpu().numpy()[:, 0] / noise).reshape(k, 1), self.dev)
+                Q = _f64(np.diag(rs), self.dev)
+                ch.solve(Q, 0)                               # L_b^-1 S^1/2
+                ch.check()
             ones = torch.ones(k, dtype=torch.float64, device=self.dev)
             for r0 in range(0, Ns, chunk):
                 r1 = min(Ns, r0 + chunk)

@@ -139,3 +139,58 @@ def test_readme_quickstart_end_to_end():
     # second fit of the process: kernel lower bound is now 1e-2 (main.py:30 vs :52)
     gp2 = RVGP.fit(d, train_ind=train_ind, epochs=5)
     assert gp2.kernel.kappa.transform.lower == 1e-2 and gp.kernel.kappa.transform.lower == 0.0
+
+
+@pytest.mark.parametrize("k", [3, 10, 20, 50, 64])
+def test_small_k_fused_kernel_matches_oracle(k):
+    """K16: fused small-k evaluation == NumPy rank-k restatement == dense GPflow-style restatement."""
+    from rvgp_b200.gp import DeviceGPR
+    g = load_golden("sphere_n2000_k50" if k <= 50 else "sphere_n2000_k50")
+    rng = np.random.default_rng(k)
+    kk = min(k, 50)
+    Phi = g["evecs_Lc"][rng.choice(6000, 153, replace=False)][:, :kk]
+    if k > kk:
+        Phi = np.concatenate([Phi, rng.normal(size=(153, k - kk))], 1)
+    lam = np.sort(np.concatenate([g["evals_Lc"][:kk], 0.7 + rng.uniform(size=k - kk)]))
+    Y = rng.normal(size=(153, 1))
+    gp = DeviceGPR(_t(Phi), _t(Y), solver="lowrank")
+    assert gp._small
+    for (nu, kappa, sf, noise) in [(1.5, 5.0, 1.0, 1.0), (2.0, 2.0, 0.5, 0.01)]:
+        S = GO.eval_S(lam, nu, kappa, sf, 6000)
+        lml, dS, dn = gp.lml_and_grads(S, noise)
+        rl, rdS, rdn = GO.gpr_lml_dense(Phi, Y, S, noise, grads=True)
+        assert abs(lml - rl) <= 1e-9 * abs(rl)
+        np.testing.assert_allclose(dS, rdS, rtol=1e-6, atol=1e-8 * np.abs(rdS).max())
+        assert abs(dn - rdn) <= 1e-6 * abs(rdn)
+        Xn = rng.normal(size=(37, k))
+        m, v = gp.predict(S, noise, _t(Xn))
+        rm, rv = GO.gpr_predict_dense(Phi, Y, S, noise, Xn)
+        np.testing.assert_allclose(m.cpu().numpy(), rm, rtol=1e-6, atol=1e-8)
+        np.testing.assert_allclose(v.cpu().numpy(), rv[:, :1], rtol=1e-6, atol=1e-9)
+
+
+def test_eeg_shaped_many_fits_on_fixed_eigenbasis():
+    """Config C3 shape: one data object, one GP fit per frame on a fixed eigenbasis (eeg_utils.py:26-35)."""
+    import time
+    import RVGP
+    from tests.workloads import make_cloud
+    from rvgp_b200 import params as P
+    X = make_cloud("scalp", 3000, 0)
+    d = RVGP.create_data_object(X, n_eigenpairs=10, verbose=False)
+    chans = RVGP.geometry.furthest_point_sampling(X, N=64)[0]
+    rng = np.random.default_rng(1)
+    Phi = d.evecs_Lc.reshape(d.n, 3, 10)
+    rest = np.setdiff1d(np.arange(d.n), chans)[:200]
+    t0 = time.perf_counter()
+    errs = []
+    for frame in range(12):
+        coef = rng.normal(size=10)
+        field = Phi @ coef                                  # (n, 3) smooth field = combination of eigenvectors
+        d.vectors = field
+        gp = RVGP.fit(d, train_ind=chans, epochs=100, noise_variance=0.001)
+        pred, var = gp.transform(d, rest.reshape(-1, 1))    # (n,1) int array as in eeg_utils.py:112
+        assert gp._gpr._small and pred.shape == (200, 3)
+        errs.append(np.linalg.norm(pred - field[rest]) / np.linalg.norm(field[rest]))
+    dt = (time.perf_counter() - t0) / 12
+    assert np.median(errs) < 0.05, errs
+    print("per-frame fit+transform: %.1f ms, median rel err %.2e" % (dt * 1e3, np.median(errs)))

@@ -149,6 +149,12 @@ int rvgp_gather_rows_f64(rvgp_handle_t h, int64_t nrows, int ncols, const double
 int rvgp_knn_f64(rvgp_handle_t h, const double* X, int n, int D, int q_begin, int q_count, int k,
                  int32_t* out_idx, double* out_d2);
 
+/* grid-accelerated exact kNN for D <= 3: identical outputs (bit for bit) to rvgp_knn_f64, candidates pruned through a
+ * uniform cell grid; lo/hi are HOST arrays (D) with the bounding box of X. */
+int rvgp_knn_grid_f64(rvgp_handle_t h, const double* X, int n, int D, const double* lo, const double* hi, int q_begin,
+                      int q_count, int k, int32_t* out_idx, double* out_d2, void* workspace, int64_t workspace_bytes);
+int64_t rvgp_knn_grid_workspace_bytes(int n, int D, const double* lo, const double* hi);
+
 /* ---- K3: kNN lists -> symmetric CSR with self loops (geometry.py:111-112, ptu_dijkstra.pyx:84-103) ----- */
 int rvgp_knn_to_csr(rvgp_handle_t h, const int32_t* knn, int n, int k, int32_t* indptr, int32_t* indices,
                     int32_t* nnz_out, void* workspace, int64_t workspace_bytes);

@@ -74,7 +74,7 @@ def _conv(a):
         return ctypes.c_uint64(int(a))
     if isinstance(a, int):
         return ctypes.c_int(a)
-    if isinstance(a, (ctypes._SimpleCData, ctypes._Pointer)):
+    if isinstance(a, (ctypes._SimpleCData, ctypes._Pointer, ctypes.Array)):
         return a
     raise TypeError("cannot pass %r to the C ABI" % type(a))
 

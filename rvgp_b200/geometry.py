@@ -44,7 +44,7 @@ class _Tensor(np.ndarray):
 # ---------------------------------------------------------------------------------------------------------
 # device building blocks
 # ---------------------------------------------------------------------------------------------------------
-def knn_device(Xd, n_neighbors, q_begin=0, q_count=None, return_d2=False):
+def knn_device(Xd, n_neighbors, q_begin=0, q_count=None, return_d2=False, method="auto"):
     """K2.  (n, D) cuda f64 -> (q_count, nb) int32 neighbour ids, ascending (distance, index)."""
     h = get_handle(Xd.device.index)
     n, D = Xd.shape
@@ -55,7 +55,19 @@ def knn_device(Xd, n_neighbors, q_begin=0, q_count=None, return_d2=False):
                          % (n_neighbors, n))
     idx = torch.empty((q_count, n_neighbors), dtype=torch.int32, device=Xd.device)
     d2 = torch.empty((q_count, n_neighbors), dtype=torch.float64, device=Xd.device) if return_d2 else None
-    h.call("rvgp_knn_f64", Xd, int(n), int(D), int(q_begin), int(q_count), int(n_neighbors), idx, d2)
+    if method == "auto":
+        method = "grid" if (D <= 3 and n >= 4096) else "brute"
+    if method == "grid":
+        import ctypes
+        mm = torch.stack([Xd.min(0).values, Xd.max(0).values]).cpu().numpy()       # bounding box (plumbing)
+        lo = (ctypes.c_double * D)(*mm[0].tolist())
+        hi = (ctypes.c_double * D)(*mm[1].tolist())
+        wsb = h.query("rvgp_knn_grid_workspace_bytes", int(n), int(D), lo, hi)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=Xd.device)
+        h.call("rvgp_knn_grid_f64", Xd, int(n), int(D), lo, hi, int(q_begin), int(q_count), int(n_neighbors), idx, d2,
+               ws, I64(wsb))
+    else:
+        h.call("rvgp_knn_f64", Xd, int(n), int(D), int(q_begin), int(q_count), int(n_neighbors), idx, d2)
     return (idx, d2) if return_d2 else idx
 
 

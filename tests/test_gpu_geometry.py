@@ -176,3 +176,26 @@ def test_data_object_matches_reference(case):
         d.smooth_vector_field(t=float(g["smooth_t"]))
         np.testing.assert_allclose(d.vectors, g["smoothed_field"], atol=1e-9)
         np.testing.assert_allclose(np.linalg.norm(d.vectors, axis=1), 1.0, atol=1e-9)
+
+
+@pytest.mark.parametrize("kind,n,D", [("torus", 20000, 3), ("sphere", 5000, 3), ("plane2", 6000, 2), ("line1", 5000, 1), ("clustered", 8000, 3)])
+def test_knn_grid_bit_identical_to_brute(kind, n, D):
+    """Grid-accelerated kNN (D <= 3) must be bit-identical to the brute-force kernel, including exact ties."""
+    from rvgp_b200 import geometry as geo
+    from tests.workloads import make_cloud
+    rng = np.random.default_rng(0)
+    if kind in ("torus", "sphere"):
+        X = make_cloud(kind, n, 0)
+    elif kind == "clustered":
+        X = np.concatenate([rng.normal(scale=0.01, size=(n // 2, 3)), rng.normal(scale=1.0, size=(n // 2, 3)) + 5.0])
+        X[10] = X[11]                                               # exact duplicate
+    else:
+        X = rng.uniform(size=(n, D))
+        X = np.round(X * 50) / 50 if kind == "plane2" else X        # lattice -> many exact distance ties
+    Xd = _t(X)
+    for k in (10, 22):
+        a, ad = geo.knn_device(Xd, k, return_d2=True, method="brute")
+        b, bd = geo.knn_device(Xd, k, return_d2=True, method="grid")
+        assert torch.equal(a, b) and torch.equal(ad, bd)
+    part = geo.knn_device(Xd, 10, q_begin=1000, q_count=777, method="grid")
+    assert torch.equal(part, geo.knn_device(Xd, 10, method="brute")[1000:1777])

@@ -131,7 +131,7 @@ dgemm_kernel(int M, int N, int64_t K, double alpha, const double* __restrict__ A
 //   A (8x4, row): a0 -> row = lane>>2, k = lane&3      B (4x8, col): b0 -> k = lane&3, n = lane>>2
 //   C/D (8x8):    c0,c1 -> row = lane>>2, cols = 2*(lane&3) + {0,1}
 // (tcgen05 has no FP64 kind; this legacy warp-level MMA is the only FP64 tensor path on sm_100a.)
-constexpr int DBN = 64, DPAD = 8;
+constexpr int DBN = 64, DPAD = 4;   // row stride = 4 (mod 16) doubles: the (k = lane&3, m = lane>>2) fragment loads are bank-conflict free
 
 __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"

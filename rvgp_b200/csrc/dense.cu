@@ -12,7 +12,7 @@ namespace rvgp {
 
 constexpr int BM = 128, BN = 128, BK = 16, PADM = 2;
 
-template <bool A_KMAJOR, bool B_KMAJOR>
+template <bool A_KMAJOR, bool B_KMAJOR, bool HAS_SCALE>
 __global__ void __launch_bounds__(256)
 dgemm_kernel(int M, int N, int64_t K, double alpha, const double* __restrict__ A, int64_t lda,
              const double* __restrict__ B, int64_t ldb, const double* __restrict__ scale_k,
@@ -34,7 +34,7 @@ dgemm_kernel(int M, int N, int64_t K, double alpha, const double* __restrict__ A
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
 
-    double ra[8], rb[8];
+    double ra[8], rb[8], rs[HAS_SCALE ? 8 : 1];
     auto load_tiles = [&](int64_t kt) {
         const int64_t k0 = kt * BK;
 #pragma unroll
@@ -44,12 +44,16 @@ dgemm_kernel(int M, int N, int64_t K, double alpha, const double* __restrict__ A
             else          { i = t & 127; k = (t >> 7) + 2 * r; }
             const int64_t gk = k0 + k;
             const int gi = m0 + i;
-            double v = 0.0;
-            if (gi < M && gk < K) {
-                v = A_KMAJOR ? __ldg(A + (int64_t)gi * lda + gk) : __ldg(A + gk * lda + gi);
-                if (scale_k) v *= __ldg(scale_k + gk);
-            }
-            ra[r] = v;
+            const bool ok = (gi < M) && (gk < K);
+            // branch-free predicated loads: all eight requests of a thread are in flight together (the first version
+            // branched per element and serialised them -- ncu: long-scoreboard stalls dominated)
+            const double* pa = A_KMAJOR ? (A + (int64_t)(ok ? gi : 0) * lda + (ok ? gk : 0)) : (A + (ok ? gk : 0) * lda + (ok ? gi : 0));
+            ra[r] = ok ? __ldg(pa) : 0.0;
+            if (HAS_SCALE) rs[r] = ok ? __ldg(scale_k + gk) : 0.0;
+        }
+        if (HAS_SCALE) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) ra[r] *= rs[r];
         }
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
@@ -58,9 +62,9 @@ dgemm_kernel(int M, int N, int64_t K, double alpha, const double* __restrict__ A
             else          { j = t & 127; k = (t >> 7) + 2 * r; }
             const int64_t gk = k0 + k;
             const int gj = n0 + j;
-            double v = 0.0;
-            if (gj < N && gk < K) v = B_KMAJOR ? __ldg(B + (int64_t)gj * ldb + gk) : __ldg(B + gk * ldb + gj);
-            rb[r] = v;
+            const bool ok = (gj < N) && (gk < K);
+            const double* pb = B_KMAJOR ? (B + (int64_t)(ok ? gj : 0) * ldb + (ok ? gk : 0)) : (B + (ok ? gk : 0) * ldb + (ok ? gj : 0));
+            rb[r] = ok ? __ldg(pb) : 0.0;
         }
     };
     auto store_tiles = [&]() {
@@ -138,7 +142,7 @@ __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, do
                  : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-template <bool A_KMAJOR, bool B_KMAJOR>
+template <bool A_KMAJOR, bool B_KMAJOR, bool HAS_SCALE>
 __global__ void __launch_bounds__(256, 2)
 dgemm_dmma_kernel(int M, int N, int64_t K, double alpha, const double* __restrict__ A, int64_t lda,
                   const double* __restrict__ B, int64_t ldb, const double* __restrict__ scale_k,
@@ -161,7 +165,7 @@ dgemm_dmma_kernel(int M, int N, int64_t K, double alpha, const double* __restric
 #pragma unroll
         for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
-    double ra[8], rb[4];
+    double ra[8], rb[4], rs[HAS_SCALE ? 8 : 1];
     auto load_tiles = [&](int64_t kt) {
         const int64_t k0 = kt * BK;
 #pragma unroll
@@ -171,12 +175,16 @@ dgemm_dmma_kernel(int M, int N, int64_t K, double alpha, const double* __restric
             else          { i = t & 127; k = (t >> 7) + 2 * r; }
             const int64_t gk = k0 + k;
             const int gi = m0 + i;
-            double v = 0.0;
-            if (gi < M && gk < K) {
-                v = A_KMAJOR ? __ldg(A + (int64_t)gi * lda + gk) : __ldg(A + gk * lda + gi);
-                if (scale_k) v *= __ldg(scale_k + gk);
-            }
-            ra[r] = v;
+            const bool ok = (gi < M) && (gk < K);
+            // branch-free predicated loads: all eight requests of a thread are in flight together (the first version
+            // branched per element and serialised them -- ncu: long-scoreboard stalls dominated)
+            const double* pa = A_KMAJOR ? (A + (int64_t)(ok ? gi : 0) * lda + (ok ? gk : 0)) : (A + (ok ? gk : 0) * lda + (ok ? gi : 0));
+            ra[r] = ok ? __ldg(pa) : 0.0;
+            if (HAS_SCALE) rs[r] = ok ? __ldg(scale_k + gk) : 0.0;
+        }
+        if (HAS_SCALE) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) ra[r] *= rs[r];
         }
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
@@ -185,9 +193,9 @@ dgemm_dmma_kernel(int M, int N, int64_t K, double alpha, const double* __restric
             else          { j = t & 63; k = (t >> 6) + 4 * r; }
             const int64_t gk = k0 + k;
             const int gj = n0 + j;
-            double v = 0.0;
-            if (gj < N && gk < K) v = B_KMAJOR ? __ldg(B + (int64_t)gj * ldb + gk) : __ldg(B + gk * ldb + gj);
-            rb[r] = v;
+            const bool ok = (gj < N) && (gk < K);
+            const double* pb = B_KMAJOR ? (B + (int64_t)(ok ? gj : 0) * ldb + (ok ? gk : 0)) : (B + (ok ? gk : 0) * ldb + (ok ? gj : 0));
+            rb[r] = ok ? __ldg(pb) : 0.0;
         }
     };
     auto store_tiles = [&]() {
@@ -356,7 +364,7 @@ int dgemm_launch(Handle* h, int m, int n, int64_t k, double alpha, const double*
     if (m == 0 || n == 0) return RVGP_OK;
     if (h->dgemm_dmma) {
         dim3 grid(cdiv(n, DBN), cdiv(m, BM), split_k);
-#define RVGP_GEMM(AK, BKM) dgemm_dmma_kernel<AK, BKM><<<grid, 256, 0, h->stream>>>(m, n, k, alpha, A, lda, B, ldb, scale_k, C, ldc, split_k, workspace, beta, lower_only)
+#define RVGP_GEMM(AK, BKM) do { if (scale_k) dgemm_dmma_kernel<AK, BKM, true><<<grid, 256, 0, h->stream>>>(m, n, k, alpha, A, lda, B, ldb, scale_k, C, ldc, split_k, workspace, beta, lower_only); else dgemm_dmma_kernel<AK, BKM, false><<<grid, 256, 0, h->stream>>>(m, n, k, alpha, A, lda, B, ldb, scale_k, C, ldc, split_k, workspace, beta, lower_only); } while (0)
         if (a_kmajor && b_kmajor) RVGP_GEMM(true, true);
         else if (a_kmajor && !b_kmajor) RVGP_GEMM(true, false);
         else if (!a_kmajor && b_kmajor) RVGP_GEMM(false, true);
@@ -364,7 +372,7 @@ int dgemm_launch(Handle* h, int m, int n, int64_t k, double alpha, const double*
 #undef RVGP_GEMM
     } else {
         dim3 grid(cdiv(n, BN), cdiv(m, BM), split_k);
-#define RVGP_GEMM(AK, BKM) dgemm_kernel<AK, BKM><<<grid, 256, 0, h->stream>>>(m, n, k, alpha, A, lda, B, ldb, scale_k, C, ldc, split_k, workspace, beta, lower_only)
+#define RVGP_GEMM(AK, BKM) do { if (scale_k) dgemm_kernel<AK, BKM, true><<<grid, 256, 0, h->stream>>>(m, n, k, alpha, A, lda, B, ldb, scale_k, C, ldc, split_k, workspace, beta, lower_only); else dgemm_kernel<AK, BKM, false><<<grid, 256, 0, h->stream>>>(m, n, k, alpha, A, lda, B, ldb, scale_k, C, ldc, split_k, workspace, beta, lower_only); } while (0)
         if (a_kmajor && b_kmajor) RVGP_GEMM(true, true);
         else if (a_kmajor && !b_kmajor) RVGP_GEMM(true, false);
         else if (!a_kmajor && b_kmajor) RVGP_GEMM(false, true);

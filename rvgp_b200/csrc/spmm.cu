@@ -107,7 +107,7 @@ bsr_spmm_kernel(int nbrows, const int* __restrict__ indptr, const int* __restric
 // loads were ~40 % of the pipe work.  With STAGE the CTA first copies the (contiguous) values and column indices of its 64
 // block rows into shared memory with coalesced loads; the inner loop then reads them with broadcast LDS (one wavefront).
 template <int D, int LPR, int CPL2, int U, bool PATTERN, bool ROT2, bool STAGE>
-__global__ void __launch_bounds__(256, (D == 2 && CPL2 == 1 && !PATTERN) ? 6 : 1)   // 40 regs, 48 warps/SM: +5 % (measured)
+__global__ void __launch_bounds__(256, (D == 2 && CPL2 == 1 && !PATTERN && !ROT2) ? 6 : 1)   // 40 regs, 48 warps/SM: +5 % (measured)
 bsr_spmm_v2_kernel(int nbrows, const int* __restrict__ indptr, const int* __restrict__ indices,
                    const double* __restrict__ vals, const double* __restrict__ X, int64_t ldx,
                    const double* __restrict__ W, int64_t ldw, double* __restrict__ Y, int64_t ldy,

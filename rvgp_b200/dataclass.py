@@ -137,7 +137,8 @@ class data:
         say('Fit connections')
         say('Compute Laplacians')
         A_Lc = BsrMatrix(n, dim_man, p_indptr, p_indices, Lc_vals_p)
-        self.stats["rot2"] = A_Lc.compress_rot2()
+        # ROT2 block storage (rvgp_bsr_compress_rot2) halves the matrix bytes but measured no faster (DESIGN.md K9 log)
+        self.stats["rot2"] = False
         A_L = BsrMatrix(n, 1, p_indptr, p_indices, None)
         self.timings["connections"] = tick() - t0
 
@@ -156,7 +157,6 @@ class data:
             plan.exchange_requests()
             S_L = ShardedBsr(plan, 1, None, comm)
             S_Lc = ShardedBsr(plan, dim_man, Lc_vals_p[plan.e0:plan.e1].contiguous(), comm)
-            S_Lc.local.compress_rot2()
             counts = [int(bounds[r + 1] - bounds[r]) for r in range(world)]
             self.stats["halo"] = dict(n_loc=plan.n_loc, n_halo=plan.n_halo, send=sum(plan.send_counts))
             evals_L, U_loc = smallest_eigenpairs(S_L, k_L, upper_bound=hi, tol=eig_tol, stats=st_L, comm=comm)

@@ -1,0 +1,90 @@
+"""Size-independent properties at BASELINE.json sizes where the reference cannot run:
+L 1 = 0, Lc symmetric with deg*I diagonal blocks, R R^T = I, orthonormal eigenvectors with small true residuals,
+exactly paired Lc eigenvalues on an orientable 2-manifold, unit-norm smoothing, K_diag == diag(K), dense == rank-k GP."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _props(n, k, check_front_end=True):
+    import RVGP
+    from rvgp_b200 import geometry as geo
+    from rvgp_b200.eigensolver import BsrMatrix
+    from tests.workloads import make_cloud
+    X = make_cloud("torus", n, 0)
+    d = RVGP.create_data_object(X, n_eigenpairs=k, verbose=False)
+    dev = d.device
+    g = d._graph
+    ip, ix = g.indptr, g.indices
+    rowlen = (ip[1:] - ip[:-1])
+    assert int(rowlen.min()) >= 11 and d.dim_man == 2
+    # graph: symmetric pattern, sorted columns, self loop present
+    rows = torch.repeat_interleave(torch.arange(n, device=dev), rowlen.long())
+    key = rows * n + ix.long()
+    keyT = ix.long() * n + rows
+    assert torch.equal(torch.sort(key).values, torch.sort(keyT).values)
+    assert bool((key[1:] > key[:-1]).all())
+    assert int((rows == ix.long()).sum()) == n
+    # connections on the ORIGINAL numbering: R R^T = I, R_ji = R_ij^T, diagonal block = deg * I
+    gauges = d.device_array("gauges")
+    Lc, R = geo.connections_device(gauges, ip, ix, want_R=True)
+    RRt = torch.einsum("eij,ekj->eik", R, R)
+    assert float((RRt - torch.eye(2, device=dev, dtype=torch.float64)).abs().max()) < 1e-12
+    diag = rows == ix.long()
+    deg = (rowlen - 1).double()
+    assert float((Lc[diag] - deg[:, None, None] * torch.eye(2, device=dev, dtype=torch.float64)).abs().max()) < 1e-10
+    # symmetry through the operator: x^T (A y) == y^T (A x); L 1 = 0
+    A = BsrMatrix(n, 2, ip, ix, Lc)
+    L = BsrMatrix(n, 1, ip, ix, None)
+    gen = torch.Generator(device=dev).manual_seed(0)
+    x = torch.randn((2 * n, 2), dtype=torch.float64, device=dev, generator=gen)
+    Ax = A.matmat(x)
+    assert abs(float((x[:, 0] * Ax[:, 1]).sum() - (x[:, 1] * Ax[:, 0]).sum())) < 1e-8 * float(Ax.abs().max()) * n ** 0.5
+    ones = torch.ones((n, 2), dtype=torch.float64, device=dev)
+    assert float(L.matmat(ones).abs().max()) == 0.0
+    # spectrum: orthonormal eigenvectors (after removing the sqrt(N) scale), true residuals, exact pairing
+    ev = torch.from_numpy(d.evals_Lc).to(dev)
+    U = d._U_Lc_p                                               # unit norm, Morton order
+    Ap = d._A_Lc_p
+    Res = Ap.matmat(U.contiguous()) - U * ev
+    hi = d.stats["eig_Lc"]["hi_gershgorin"]
+    assert float(torch.linalg.vector_norm(Res, dim=0).max()) <= 2e-12 * hi
+    G = U.T @ U
+    assert float((G - torch.eye(k, device=dev, dtype=torch.float64)).abs().max()) < 1e-10
+    e = d.evals_Lc
+    assert np.all(np.diff(e) >= -1e-12) and e[0] > 0
+    pairs = np.abs(e[0:k - 1:2] - e[1:k:2]) / e[1:k:2]
+    assert pairs.max() < 1e-8, pairs.max()                       # orientable 2-manifold: degenerate pairs
+    eL = d.evals_L
+    assert abs(eL[0]) < 1e-8 * hi and np.all(np.diff(eL) >= -1e-12)
+    # lifted eigenvectors: evecs_Lc^T evecs_Lc = N_Lc * I (gauges are orthonormal frames)
+    Phi = d.device_array("evecs_Lc")
+    assert float(((Phi.T @ Phi) / (2 * n) - torch.eye(k, device=dev, dtype=torch.float64)).abs().max()) < 1e-9
+    # smoothing keeps unit norm; GP: K_diag == diag(K) and dense == rank-k on a subsample
+    d.random_vector_field(seed=1)
+    d.smooth_vector_field(t=100)
+    nv = torch.linalg.vector_norm(d.device_array("vectors"), dim=1)
+    assert float((nv - 1).abs().max()) < 1e-9
+    kern = RVGP.kernels.ManifoldKernel(d, nu=1.5, kappa=5.0, sigma_f=1.0)
+    rows_s = Phi[:: max(1, (3 * n) // 1500)][:1500]
+    Kd = kern.K_diag(rows_s)
+    Kf = kern.K(rows_s)
+    assert float((Kd - torch.diagonal(Kf)).abs().max()) <= 1e-12 * float(Kd.abs().max())
+    from rvgp_b200.gp import DeviceGPR
+    y = d.device_array("vectors").reshape(-1, 1)[:: max(1, (3 * n) // 1500)][:1500].contiguous()
+    S = kern.eval_S()
+    a = DeviceGPR(rows_s.contiguous(), y, solver="dense").lml_and_grads(S, 0.3)
+    b = DeviceGPR(rows_s.contiguous(), y, solver="lowrank").lml_and_grads(S, 0.3)
+    assert abs(a[0] - b[0]) <= 1e-9 * abs(a[0])
+    np.testing.assert_allclose(a[1], b[1], rtol=1e-6, atol=1e-8 * np.abs(a[1]).max())
+    return d
+
+
+def test_properties_c2_size():
+    _props(35000, 200)
+
+
+def test_properties_200k():
+    _props(200000, 100)

@@ -111,13 +111,21 @@ __global__ void __launch_bounds__(256, (D == 2 && CPL2 == 1 && !PATTERN && !ROT2
 bsr_spmm_v2_kernel(int nbrows, const int* __restrict__ indptr, const int* __restrict__ indices,
                    const double* __restrict__ vals, const double* __restrict__ X, int64_t ldx,
                    const double* __restrict__ W, int64_t ldw, double* __restrict__ Y, int64_t ldy,
-                   int ncols, double alpha, double beta, double gamma, int rows_per_group, int stage_cap) {
+                   int ncols, double alpha, double beta, double gamma, int rows_per_group, int stage_cap, int nsm) {
     constexpr int GPW = 32 / LPR;
     constexpr int VB = ROT2 ? 2 : D * D;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane / LPR, l = lane % LPR;
     const int rows_per_cta = 8 * GPW * rows_per_group;
-    const int row0 = blockIdx.x * rows_per_cta;
+    // SM-contiguous chunk order: the block scheduler hands blockIdx b, b+nsm, b+2*nsm, ... to the same SM, so mapping
+    // them to CONSECUTIVE row chunks makes the CTAs that share an L1 work on adjacent (Morton-neighbouring) rows.
+    int chunk = blockIdx.x;
+    if (nsm > 0) {
+        const int per = gridDim.x / nsm;
+        chunk = (blockIdx.x % nsm) * per + blockIdx.x / nsm;
+    }
+    const int row0 = chunk * rows_per_cta;
+    if (row0 >= nbrows) return;
     const int npairs = ncols >> 1;
     extern __shared__ __align__(16) double stage_smem[];
     double* svals = stage_smem;
@@ -257,17 +265,20 @@ static int launch_spmm_v2(Handle* h, int nbrows, const int* indptr, const int* i
     do {                                                                                                   \
         constexpr int U = (D * CPL2 <= 2) ? 4 : ((D * CPL2 <= 4) ? 2 : 1);                                 \
         const int rows_per_cta = 8 * (32 / LPR) * rpg;                                                     \
+        const int nchunks_ = cdiv(nbrows, rows_per_cta);                                                   \
+        const int nsm_ = (h->spmm_remap && nchunks_ >= 4 * h->sm_count) ? h->sm_count : 0;                 \
+        const int grid_ = nsm_ ? cdiv(nchunks_, nsm_) * nsm_ : nchunks_;                                   \
         if (!PATTERN && h->spmm_stage) {                                                                   \
             constexpr int VB_ = ROT2 ? 2 : D * D;                                                          \
             const int cap = rows_per_cta * 16;                                                             \
             const int smem = cap * (VB_ * 8 + 4);                                                          \
             auto kern = bsr_spmm_v2_kernel<D, LPR, CPL2, U, PATTERN, ROT2, true>;                          \
             if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
-            kern<<<cdiv(nbrows, rows_per_cta), 256, smem, h->stream>>>(                                    \
-                nbrows, indptr, indices, vals, X, ldx, W, ldw, Y, ldy, ncols, alpha, beta, gamma, rpg, cap); \
+            kern<<<grid_, 256, smem, h->stream>>>(                                                         \
+                nbrows, indptr, indices, vals, X, ldx, W, ldw, Y, ldy, ncols, alpha, beta, gamma, rpg, cap, nsm_); \
         } else {                                                                                           \
-            bsr_spmm_v2_kernel<D, LPR, CPL2, U, PATTERN, ROT2, false><<<cdiv(nbrows, rows_per_cta), 256, 0, h->stream>>>( \
-                nbrows, indptr, indices, vals, X, ldx, W, ldw, Y, ldy, ncols, alpha, beta, gamma, rpg, 0); \
+            bsr_spmm_v2_kernel<D, LPR, CPL2, U, PATTERN, ROT2, false><<<grid_, 256, 0, h->stream>>>(       \
+                nbrows, indptr, indices, vals, X, ldx, W, ldw, Y, ldy, ncols, alpha, beta, gamma, rpg, 0, nsm_); \
         }                                                                                                  \
     } while (0)
     int lpr = h->spmm_lpr;

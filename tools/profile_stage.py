@@ -22,9 +22,9 @@ for b in (32, 64):
     for rot in (False,):
         A.d_code = A.d
         if rot: A.compress_rot2()
-        for stage in (0,):
-            h.set_option("spmm_stage", stage)
-            for lpr in (0, 16, 32):
+        for stage in (0, 1):
+            h.set_option("spmm_remap", stage)
+            for lpr in (0,):
                 h.set_option("spmm_lpr", lpr)
                 t = bench(A, X, W, Y1 if (stage or rot) else Y0)
-                print("Lc b=%d rot2=%s stage=%d lpr=%d: %.4f ms frac %.3f  maxdiff %.1e" % (b, rot, stage, lpr, t, by / t / 1e6 / 6534.5, float((Y0 - Y1).abs().max()) if (stage or rot) else 0.0))
+                print("Lc b=%d rot2=%s remap=%d lpr=%d: %.4f ms frac %.3f  maxdiff %.1e" % (b, rot, stage, lpr, t, by / t / 1e6 / 6534.5, float((Y0 - Y1).abs().max()) if (stage or rot) else 0.0))

@@ -194,3 +194,19 @@ def test_eeg_shaped_many_fits_on_fixed_eigenbasis():
     dt = (time.perf_counter() - t0) / 12
     assert np.median(errs) < 0.05, errs
     print("per-frame fit+transform: %.1f ms, median rel err %.2e" % (dt * 1e3, np.median(errs)))
+
+
+def test_transform_with_float_positional_encodings():
+    """main.py:108-109 / README.md:110: float test_ind = positional encodings (rows of the spectral embedding)."""
+    import RVGP
+    g = load_golden("torus_n600_k20")
+    d = RVGP.create_data_object(g["X"], n_eigenpairs=20, verbose=False)
+    d.vectors = g["smoothed_field"]
+    gp = RVGP.fit(d, train_ind=np.arange(0, 600, 2), epochs=50)
+    nodes = np.arange(1, 600, 2)[:40]
+    m_int, v_int = gp.transform(d, [int(i) for i in nodes])
+    enc = d.evecs_Lc.reshape(d.n, -1)[nodes].reshape(-1, 20)           # (40*3, k) float rows
+    m_f, v_f = gp.transform(d, enc)
+    assert m_f.shape == (120, 1)
+    np.testing.assert_allclose(m_f.reshape(40, 3), m_int, rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(v_f.reshape(40, 3), v_int, rtol=1e-12, atol=1e-14)

@@ -54,6 +54,13 @@ int rvgp_bsr_spmm_f64(rvgp_handle_t h, int nbrows, int d, const int32_t* indptr,
                       const double* vals, const double* X, int64_t ldx, const double* W, int64_t ldw,
                       double* Y, int64_t ldy, int ncols, double alpha, double beta, double gamma);
 
+/* rvgp_bsr_spmm_f64 restricted to the block rows in rowlist (nlist entries); the other rows of Y are untouched.
+ * Recomputes the boundary rows of a row-sharded matrix once the halo exchange has landed (the full launch overlaps it). */
+int rvgp_bsr_spmm_rows_f64(rvgp_handle_t h, int nbrows, int d, const int32_t* indptr, const int32_t* indices,
+                           const double* vals, const double* X, int64_t ldx, const double* W, int64_t ldw, double* Y,
+                           int64_t ldy, int ncols, double alpha, double beta, double gamma, const int32_t* rowlist,
+                           int nlist);
+
 /* ROT2 storage for d == 2: when every block is a scaled 2x2 orthogonal matrix [[a,-s*b],[b,s*a]] (true for the
  * connection Laplacian: Procrustes blocks, diagonal deg*I) it is stored as (a,b) with s in the sign bit of the column
  * index -- half the matrix bytes and half the value loads.  bad_flag (device int32): bit0 set if some block does not

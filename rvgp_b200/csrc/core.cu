@@ -16,6 +16,8 @@ extern "C" int rvgp_create(int device, rvgp_handle_t* out) {
     h->launches = 0;
     h->spmm_lpr = 0;
     h->spmm_v1 = 0;
+    h->rowlist = nullptr;
+    h->nlist = 0;
     h->spmm_remap = 0;   // measured: no gain (DESIGN.md K9 log)
     h->spmm_stage = 0;   // measured: no gain (tools/profile_stage.py); value loads are not the limiter
     h->dgemm_dmma = 1;   // measured on B200: 17 vs 14 TFLOP/s for the tall-skinny Gram (tools/ncu_dgemm.py)

@@ -111,7 +111,8 @@ __global__ void __launch_bounds__(256, (D == 2 && CPL2 == 1 && !PATTERN && !ROT2
 bsr_spmm_v2_kernel(int nbrows, const int* __restrict__ indptr, const int* __restrict__ indices,
                    const double* __restrict__ vals, const double* __restrict__ X, int64_t ldx,
                    const double* __restrict__ W, int64_t ldw, double* __restrict__ Y, int64_t ldy,
-                   int ncols, double alpha, double beta, double gamma, int rows_per_group, int stage_cap, int nsm) {
+                   int ncols, double alpha, double beta, double gamma, int rows_per_group, int stage_cap, int nsm,
+                   const int* __restrict__ rowlist, int nlist) {
     constexpr int GPW = 32 / LPR;
     constexpr int VB = ROT2 ? 2 : D * D;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -125,7 +126,7 @@ bsr_spmm_v2_kernel(int nbrows, const int* __restrict__ indptr, const int* __rest
         chunk = (blockIdx.x % nsm) * per + blockIdx.x / nsm;
     }
     const int row0 = chunk * rows_per_cta;
-    if (row0 >= nbrows) return;
+    if (row0 >= (rowlist ? nlist : nbrows)) return;
     const int npairs = ncols >> 1;
     extern __shared__ __align__(16) double stage_smem[];
     double* svals = stage_smem;
@@ -149,8 +150,9 @@ bsr_spmm_v2_kernel(int nbrows, const int* __restrict__ indptr, const int* __rest
     for (int cc = 0; cc < CPL2; ++cc) colok[cc] = (l + LPR * cc) < npairs;
 
     for (int it = 0; it < rows_per_group; ++it) {
-        const int i = row0 + it * (8 * GPW) + warp * GPW + g;
-        if (i >= nbrows) continue;
+        const int vi = row0 + it * (8 * GPW) + warp * GPW + g;
+        if (vi >= (rowlist ? nlist : nbrows)) continue;
+        const int i = rowlist ? __ldg(rowlist + vi) : vi;      // optional row list (boundary rows of a row-sharded matrix)
         const int e0 = __ldg(indptr + i), e1 = __ldg(indptr + i + 1);
         double2 acc[D][CPL2];
 #pragma unroll
@@ -265,20 +267,20 @@ static int launch_spmm_v2(Handle* h, int nbrows, const int* indptr, const int* i
     do {                                                                                                   \
         constexpr int U = (D * CPL2 <= 2) ? 4 : ((D * CPL2 <= 4) ? 2 : 1);                                 \
         const int rows_per_cta = 8 * (32 / LPR) * rpg;                                                     \
-        const int nchunks_ = cdiv(nbrows, rows_per_cta);                                                   \
+        const int nchunks_ = cdiv(h->rowlist ? h->nlist : nbrows, rows_per_cta);                           \
         const int nsm_ = (h->spmm_remap && nchunks_ >= 4 * h->sm_count) ? h->sm_count : 0;                 \
         const int grid_ = nsm_ ? cdiv(nchunks_, nsm_) * nsm_ : nchunks_;                                   \
-        if (!PATTERN && h->spmm_stage) {                                                                   \
+        if (!PATTERN && h->spmm_stage && !h->rowlist) {                                                    \
             constexpr int VB_ = ROT2 ? 2 : D * D;                                                          \
             const int cap = rows_per_cta * 16;                                                             \
             const int smem = cap * (VB_ * 8 + 4);                                                          \
             auto kern = bsr_spmm_v2_kernel<D, LPR, CPL2, U, PATTERN, ROT2, true>;                          \
             if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
             kern<<<grid_, 256, smem, h->stream>>>(                                                         \
-                nbrows, indptr, indices, vals, X, ldx, W, ldw, Y, ldy, ncols, alpha, beta, gamma, rpg, cap, nsm_); \
+                nbrows, indptr, indices, vals, X, ldx, W, ldw, Y, ldy, ncols, alpha, beta, gamma, rpg, cap, nsm_, h->rowlist, h->nlist); \
         } else {                                                                                           \
             bsr_spmm_v2_kernel<D, LPR, CPL2, U, PATTERN, ROT2, false><<<grid_, 256, 0, h->stream>>>(       \
-                nbrows, indptr, indices, vals, X, ldx, W, ldw, Y, ldy, ncols, alpha, beta, gamma, rpg, 0, nsm_); \
+                nbrows, indptr, indices, vals, X, ldx, W, ldw, Y, ldy, ncols, alpha, beta, gamma, rpg, 0, nsm_, h->rowlist, h->nlist); \
         }                                                                                                  \
     } while (0)
     int lpr = h->spmm_lpr;
@@ -347,6 +349,7 @@ static int spmm_dispatch(Handle* h, int nbrows, int d, const int* indptr, const 
                          (vals == nullptr || (uintptr_t)vals % 16 == 0);
     RVGP_REQUIRE(h, ncols <= 64 || aligned0, "spmm: more than 64 columns needs the 128-bit path (even ncols / ld, 16-byte alignment)");
     const bool aligned = aligned0 && (!h->spmm_v1 || ncols > 64);
+    RVGP_REQUIRE(h, h->rowlist == nullptr || aligned, "spmm: a row list needs the 128-bit path (even ncols / ld, 16-byte alignment)");
     if (d == -2) {   // ROT2-compressed 2x2 blocks (see rvgp_bsr_compress_rot2)
         RVGP_REQUIRE(h, aligned && vals != nullptr, "spmm: rot2 storage needs even ncols / leading dimensions and 16-byte aligned buffers");
         return launch_spmm_v2<2, false, true>(h, nbrows, indptr, indices, vals, X, ldx, W, ldw, Y, ldy, ncols, alpha, beta, gamma);
@@ -375,6 +378,23 @@ static int spmm_dispatch(Handle* h, int nbrows, int d, const int* indptr, const 
 }  // namespace rvgp
 
 using namespace rvgp;
+
+// Same as rvgp_bsr_spmm_f64 restricted to the block rows listed in `rowlist` (nlist entries); other rows of Y are left
+// untouched.  Used to recompute the boundary rows of a row-sharded matrix after the halo exchange has landed, while the
+// full launch overlapped the exchange (rvgp_b200/distributed.py).
+extern "C" int rvgp_bsr_spmm_rows_f64(rvgp_handle_t hh, int nbrows, int d, const int32_t* indptr, const int32_t* indices,
+                                      const double* vals, const double* X, int64_t ldx, const double* W, int64_t ldw,
+                                      double* Y, int64_t ldy, int ncols, double alpha, double beta, double gamma,
+                                      const int32_t* rowlist, int nlist) {
+    Handle* h = H(hh);
+    if (nlist <= 0) return RVGP_OK;
+    h->rowlist = rowlist;
+    h->nlist = nlist;
+    const int rc = spmm_dispatch(h, nbrows, d, indptr, indices, vals, X, ldx, W, ldw, Y, ldy, ncols, alpha, beta, gamma);
+    h->rowlist = nullptr;
+    h->nlist = 0;
+    return rc;
+}
 
 extern "C" int rvgp_bsr_spmm_f64(rvgp_handle_t hh, int nbrows, int d, const int32_t* indptr, const int32_t* indices,
                                  const double* vals, const double* X, int64_t ldx, const double* W, int64_t ldw,

@@ -46,6 +46,10 @@ class HaloPlan:
         # renumber: local -> col - r0 ; halo -> n_loc + position in the sorted halo list
         pos = torch.searchsorted(halo, cols.clamp(min=0)) if self.n_halo else torch.zeros_like(cols)
         self.indices_loc = torch.where(outside, pos + self.n_loc, cols - r0).to(torch.int32).contiguous()
+        # block rows that reference at least one halo column (they need the exchanged data; all others do not)
+        rowlen = (self.indptr_loc[1:] - self.indptr_loc[:-1]).to(torch.int64)
+        rowid = torch.repeat_interleave(torch.arange(self.n_loc, device=dev), rowlen)
+        self.boundary_rows = torch.unique(rowid[outside]).to(torch.int32).contiguous()
         # how many halo nodes come from each peer
         b = torch.tensor(self.bounds, dtype=torch.int64, device=dev)
         owner = torch.searchsorted(b, halo, right=True) - 1 if self.n_halo else halo
@@ -78,12 +82,28 @@ class HaloPlan:
         ids = torch.cat([recv_bufs[q] for q in range(self.world)]) if sum(self.send_counts) else torch.zeros(0, dtype=torch.int64, device=dev)
         self.send_ids = (ids - self.r0).to(torch.int32).contiguous()
 
+    def exchange_async(self, ext, pack_fn, d):
+        """Start the halo exchange (NCCL) and return a handle to wait on; None when there is nothing to do."""
+        if self.world == 1 or (self.n_halo == 0 and self.send_ids.numel() == 0) or not ext.is_cuda:
+            self.exchange(ext, pack_fn, d)
+            return None
+        sendbuf = pack_fn(ext[: self.n_loc * d], self.send_ids, d)
+        return dist.all_to_all_single(ext[self.n_loc * d:], sendbuf,
+                                      output_split_sizes=[c * d for c in self.recv_counts],
+                                      input_split_sizes=[c * d for c in self.send_counts], group=self.group, async_op=True)
+
     def exchange(self, ext, pack_fn, d):
         """Fill the halo slice ext[n_loc*d:] of the extended block vector (rows x b, contiguous) from the peers.
         pack_fn(ext_local, send_ids, d) -> (n_send*d, b) contiguous tensor of the rows to ship."""
         if self.world == 1 or (self.n_halo == 0 and self.send_ids.numel() == 0):
             return
         sendbuf = pack_fn(ext[: self.n_loc * d], self.send_ids, d)
+        if ext.is_cuda:
+            # NCCL: one all-to-all with uneven splits (rows per peer) instead of 2*(P-1) point-to-point ops
+            dist.all_to_all_single(ext[self.n_loc * d:], sendbuf,
+                                   output_split_sizes=[c * d for c in self.recv_counts],
+                                   input_split_sizes=[c * d for c in self.send_counts], group=self.group)
+            return
         ops, soff, roff = [], 0, self.n_loc * d
         for q in range(self.world):
             sc, rc = self.send_counts[q] * d, self.recv_counts[q] * d
@@ -142,9 +162,11 @@ class ShardedBsr:
         return self.local.spmm_bytes(ncols, fused)
 
     def _pack(self, ext_local, send_ids, d):
-        from .geometry import gather_rows_device
         n_send = int(send_ids.numel())
-        out = torch.empty((n_send * d, ext_local.shape[1]), dtype=ext_local.dtype, device=ext_local.device)
+        key = ("pack", ext_local.shape[1])
+        if key not in self._bufs:
+            self._bufs[key] = torch.empty((n_send * d, ext_local.shape[1]), dtype=ext_local.dtype, device=ext_local.device)
+        out = self._bufs[key]
         if n_send:
             from ._cabi import get_handle, I64
             h = get_handle(ext_local.device.index)
@@ -158,6 +180,31 @@ class ShardedBsr:
             self._bufs[key] = torch.zeros((self.ext_rows, ncols), dtype=torch.float64, device=self.indptr.device)
         return self._bufs[key]
 
+    def _spmm_overlapped(self, E_in, E_out, alpha=1.0, beta=0.0, gamma=0.0, W=None, h=None):
+        """E_out[:local] = alpha*A*E_in + beta*E_in + gamma*W with the halo exchange of E_in hidden behind the SpMM:
+        the full launch runs while the exchange is in flight (its boundary rows read stale halo data and are
+        discarded), then only the boundary rows are recomputed once the halo has landed."""
+        from ._cabi import get_handle, I64
+        h = h or get_handle(E_in.device.index)
+        ncols = E_in.shape[1]
+        nb = int(self.plan.boundary_rows.numel())
+        can_overlap = (self.overlap and nb > 0 and ncols % 2 == 0 and nb * 4 < self.plan.n_loc)
+        if not can_overlap:
+            self.plan.exchange(E_in, self._pack, self.d)
+            self.local.spmm(E_in, E_out[: self.nrows], alpha=alpha, beta=beta, gamma=gamma, W=W, h=h)
+            return
+        work = self.plan.exchange_async(E_in, self._pack, self.d)
+        self.local.spmm(E_in, E_out[: self.nrows], alpha=alpha, beta=beta, gamma=gamma, W=W, h=h)
+        if work is not None:
+            work.wait()
+        L = self.local
+        Yv = E_out[: self.nrows]
+        h.call("rvgp_bsr_spmm_rows_f64", L.nbrows, L.d, L.indptr, L.indices, L.vals, E_in, I64(E_in.stride(0)), W,
+               I64(W.stride(0) if W is not None else 0), Yv, I64(Yv.stride(0)), int(ncols), float(alpha), float(beta),
+               float(gamma), self.plan.boundary_rows, nb)
+
+    overlap = True
+
     def matmat(self, X, out=None, h=None):
         if out is None:
             out = torch.empty_like(X)
@@ -165,9 +212,8 @@ class ShardedBsr:
             c1 = min(X.shape[1], c0 + 64)
             E = self._ext(c1 - c0, 0)
             E[: self.nrows].copy_(X[:, c0:c1])
-            self.plan.exchange(E, self._pack, self.d)
             tmp = self._ext(c1 - c0, 1)
-            self.local.spmm(E, tmp[: self.nrows], h=h)
+            self._spmm_overlapped(E, tmp, h=h)
             out[:, c0:c1].copy_(tmp[: self.nrows])
         return out
 
@@ -180,14 +226,12 @@ class ShardedBsr:
         e, c = 0.5 * (hi - lo_cut), 0.5 * (hi + lo_cut)
         sigma1 = e / (lo_spec - c)
         tau, sigma = 2.0 / sigma1, sigma1
-        self.plan.exchange(E[0], self._pack, self.d)
-        self.local.spmm(E[0], E[1][: self.nrows], alpha=sigma1 / e, beta=-c * sigma1 / e, h=h)
+        self._spmm_overlapped(E[0], E[1], alpha=sigma1 / e, beta=-c * sigma1 / e, h=h)
         prev, cur = 0, 1
         for _ in range(2, degree + 1):
             sn = 1.0 / (tau - sigma)
             nxt = 3 - prev - cur
-            self.plan.exchange(E[cur], self._pack, self.d)
-            self.local.spmm(E[cur], E[nxt][: self.nrows], alpha=2.0 * sn / e, beta=-2.0 * sn * c / e, gamma=-sigma * sn,
-                            W=E[prev][: self.nrows], h=h)
+            self._spmm_overlapped(E[cur], E[nxt], alpha=2.0 * sn / e, beta=-2.0 * sn * c / e, gamma=-sigma * sn,
+                                  W=E[prev][: self.nrows], h=h)
             sigma, prev, cur = sn, cur, nxt
         Vp.copy_(E[cur][: self.nrows])

@@ -19,7 +19,6 @@ struct Handle {
     int spmm_v1;                  // tuning: force the 64-bit-load kernel
     const int* rowlist;           // transient: row list of rvgp_bsr_spmm_rows_f64
     int nlist;
-    int spmm_remap;               // tuning: SM-contiguous chunk order in the SpMM
     int spmm_stage;               // tuning: stage block values / indices of a CTA's rows in shared memory
     int dgemm_dmma;               // tuning: FP64 tensor (mma.sync m8n8k4) instead of the DFMA register tile
 };

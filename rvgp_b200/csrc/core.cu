@@ -18,7 +18,6 @@ extern "C" int rvgp_create(int device, rvgp_handle_t* out) {
     h->spmm_v1 = 0;
     h->rowlist = nullptr;
     h->nlist = 0;
-    h->spmm_remap = 0;   // measured: no gain (DESIGN.md K9 log)
     h->spmm_stage = 0;   // measured: no gain (tools/profile_stage.py); value loads are not the limiter
     h->dgemm_dmma = 1;   // measured on B200: 17 vs 14 TFLOP/s for the tall-skinny Gram (tools/ncu_dgemm.py)
     h->last_error[0] = 0;
@@ -48,7 +47,6 @@ extern "C" unsigned long long rvgp_launch_count(rvgp_handle_t hh) { return hh ? 
 extern "C" int rvgp_set_option(rvgp_handle_t hh, const char* key, int value) {
     if (!hh || !key) return RVGP_ERR_BAD_ARG;
     if (strcmp(key, "spmm_lpr") == 0) { H(hh)->spmm_lpr = value; return RVGP_OK; }
-    if (strcmp(key, "spmm_remap") == 0) { H(hh)->spmm_remap = value; return RVGP_OK; }
     if (strcmp(key, "spmm_v1") == 0) { H(hh)->spmm_v1 = value; return RVGP_OK; }
     if (strcmp(key, "spmm_stage") == 0) { H(hh)->spmm_stage = value; return RVGP_OK; }
     if (strcmp(key, "dgemm_dmma") == 0) { H(hh)->dgemm_dmma = value; return RVGP_OK; }

@@ -106,27 +106,19 @@ bsr_spmm_kernel(int nbrows, const int* __restrict__ indptr, const int* __restric
 // STAGE: a warp-uniform LDG.128 still costs four L1 data-pipe wavefronts (quarter-warp granularity), so the per-block value
 // loads were ~40 % of the pipe work.  With STAGE the CTA first copies the (contiguous) values and column indices of its 64
 // block rows into shared memory with coalesced loads; the inner loop then reads them with broadcast LDS (one wavefront).
-template <int D, int LPR, int CPL2, int U, bool PATTERN, bool ROT2, bool STAGE>
-__global__ void __launch_bounds__(256, (D == 2 && CPL2 == 1 && !PATTERN && !ROT2) ? 6 : 1)   // 40 regs, 48 warps/SM: +5 % (measured)
+template <int D, int LPR, int CPL2, int U, bool PATTERN, bool ROT2, bool STAGE, bool ROWLIST>
+__global__ void __launch_bounds__(256, (D == 2 && CPL2 == 1 && !PATTERN && !ROT2 && !STAGE && !ROWLIST) ? 6 : 1)   // 40 regs, 48 warps/SM: +5 % (measured)
 bsr_spmm_v2_kernel(int nbrows, const int* __restrict__ indptr, const int* __restrict__ indices,
                    const double* __restrict__ vals, const double* __restrict__ X, int64_t ldx,
                    const double* __restrict__ W, int64_t ldw, double* __restrict__ Y, int64_t ldy,
-                   int ncols, double alpha, double beta, double gamma, int rows_per_group, int stage_cap, int nsm,
+                   int ncols, double alpha, double beta, double gamma, int rows_per_group, int stage_cap,
                    const int* __restrict__ rowlist, int nlist) {
     constexpr int GPW = 32 / LPR;
     constexpr int VB = ROT2 ? 2 : D * D;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane / LPR, l = lane % LPR;
     const int rows_per_cta = 8 * GPW * rows_per_group;
-    // SM-contiguous chunk order: the block scheduler hands blockIdx b, b+nsm, b+2*nsm, ... to the same SM, so mapping
-    // them to CONSECUTIVE row chunks makes the CTAs that share an L1 work on adjacent (Morton-neighbouring) rows.
-    int chunk = blockIdx.x;
-    if (nsm > 0) {
-        const int per = gridDim.x / nsm;
-        chunk = (blockIdx.x % nsm) * per + blockIdx.x / nsm;
-    }
-    const int row0 = chunk * rows_per_cta;
-    if (row0 >= (rowlist ? nlist : nbrows)) return;
+    const int row0 = blockIdx.x * rows_per_cta;
     const int npairs = ncols >> 1;
     extern __shared__ __align__(16) double stage_smem[];
     double* svals = stage_smem;
@@ -151,8 +143,8 @@ bsr_spmm_v2_kernel(int nbrows, const int* __restrict__ indptr, const int* __rest
 
     for (int it = 0; it < rows_per_group; ++it) {
         const int vi = row0 + it * (8 * GPW) + warp * GPW + g;
-        if (vi >= (rowlist ? nlist : nbrows)) continue;
-        const int i = rowlist ? __ldg(rowlist + vi) : vi;      // optional row list (boundary rows of a row-sharded matrix)
+        if (vi >= (ROWLIST ? nlist : nbrows)) continue;
+        const int i = ROWLIST ? __ldg(rowlist + vi) : vi;      // optional row list (boundary rows of a row-sharded matrix)
         const int e0 = __ldg(indptr + i), e1 = __ldg(indptr + i + 1);
         double2 acc[D][CPL2];
 #pragma unroll
@@ -267,20 +259,21 @@ static int launch_spmm_v2(Handle* h, int nbrows, const int* indptr, const int* i
     do {                                                                                                   \
         constexpr int U = (D * CPL2 <= 2) ? 4 : ((D * CPL2 <= 4) ? 2 : 1);                                 \
         const int rows_per_cta = 8 * (32 / LPR) * rpg;                                                     \
-        const int nchunks_ = cdiv(h->rowlist ? h->nlist : nbrows, rows_per_cta);                           \
-        const int nsm_ = (h->spmm_remap && nchunks_ >= 4 * h->sm_count) ? h->sm_count : 0;                 \
-        const int grid_ = nsm_ ? cdiv(nchunks_, nsm_) * nsm_ : nchunks_;                                   \
-        if (!PATTERN && h->spmm_stage && !h->rowlist) {                                                    \
+        const int grid_ = cdiv(h->rowlist ? h->nlist : nbrows, rows_per_cta);                              \
+        if (h->rowlist) {                                                                                  \
+            bsr_spmm_v2_kernel<D, LPR, CPL2, U, PATTERN, ROT2, false, true><<<grid_, 256, 0, h->stream>>>( \
+                nbrows, indptr, indices, vals, X, ldx, W, ldw, Y, ldy, ncols, alpha, beta, gamma, rpg, 0, h->rowlist, h->nlist); \
+        } else if (!PATTERN && h->spmm_stage) {                                                            \
             constexpr int VB_ = ROT2 ? 2 : D * D;                                                          \
             const int cap = rows_per_cta * 16;                                                             \
             const int smem = cap * (VB_ * 8 + 4);                                                          \
-            auto kern = bsr_spmm_v2_kernel<D, LPR, CPL2, U, PATTERN, ROT2, true>;                          \
+            auto kern = bsr_spmm_v2_kernel<D, LPR, CPL2, U, PATTERN, ROT2, true, false>;                   \
             if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
             kern<<<grid_, 256, smem, h->stream>>>(                                                         \
-                nbrows, indptr, indices, vals, X, ldx, W, ldw, Y, ldy, ncols, alpha, beta, gamma, rpg, cap, nsm_, h->rowlist, h->nlist); \
+                nbrows, indptr, indices, vals, X, ldx, W, ldw, Y, ldy, ncols, alpha, beta, gamma, rpg, cap, nullptr, 0); \
         } else {                                                                                           \
-            bsr_spmm_v2_kernel<D, LPR, CPL2, U, PATTERN, ROT2, false><<<grid_, 256, 0, h->stream>>>(       \
-                nbrows, indptr, indices, vals, X, ldx, W, ldw, Y, ldy, ncols, alpha, beta, gamma, rpg, 0, nsm_, h->rowlist, h->nlist); \
+            bsr_spmm_v2_kernel<D, LPR, CPL2, U, PATTERN, ROT2, false, false><<<grid_, 256, 0, h->stream>>>( \
+                nbrows, indptr, indices, vals, X, ldx, W, ldw, Y, ldy, ncols, alpha, beta, gamma, rpg, 0, nullptr, 0); \
         }                                                                                                  \
     } while (0)
     int lpr = h->spmm_lpr;

@@ -270,6 +270,8 @@ def smallest_eigenpairs(A, k, upper_bound, lower_bound=0.0, tol=1e-12, nex=None,
     m = min(Nglob, k + nex)
     if panel is None:
         panel = 64 if m >= 128 else 32
+        if getattr(A, "vals", 1) is None and m >= 512 and comm is None:
+            panel = 128        # scalar pattern-mode Laplacian: 0.57 vs 0.52 of HBM peak with 128-column panels (measured)
     if m < Nglob:
         m = min(Nglob, ((m + panel - 1) // panel) * panel)
     hi = float(upper_bound)

@@ -22,3 +22,20 @@ def test_no_cpu_fallback_without_gpu():
         pytest.skip("GPU present")
     with pytest.raises(RuntimeError):
         _cabi.Handle(0)
+
+
+def test_hot_spmm_kernel_does_not_spill():
+    """The d=2 / 64-column fused SpMM instantiation is register-capped (6 CTAs/SM); extra kernel parameters once pushed
+    it into local-memory spills and cost 25 % -- keep that from regressing silently (ptxas -v log of the build)."""
+    import os
+    import re
+    import __graft_entry__ as g
+    g.build()
+    log = os.path.join(os.path.dirname(_cabi.LIB_PATH), "..", "build", "spmm.o.log")
+    txt = open(log).read()
+    i = txt.find("Function properties for _ZN4rvgp18bsr_spmm_v2_kernelILi2ELi32ELi1ELi4ELb0ELb0ELb0ELb0E")
+    assert i >= 0, "hot instantiation not found in the ptxas log"
+    chunk = txt[i:i + 600]
+    assert "0 bytes spill stores, 0 bytes spill loads" in chunk, chunk
+    regs = int(re.search(r"Used (\d+) registers", chunk).group(1))
+    assert regs <= 40

@@ -196,6 +196,11 @@ int rvgp_slice_frames(rvgp_handle_t h, const double* T, int64_t n, int D, int df
 int rvgp_connections(rvgp_handle_t h, const double* gauges, int n, int D, int d, const int32_t* indptr,
                      const int32_t* indices, int64_t nnzb, double* Lc_vals, double* R_vals);
 
+/* initial block for the Lc eigensolver built from scalar-Laplacian eigenvectors U (n x kL):
+ * out[(i*d+q), c] = gauges[i][c % D][q] * U[i][c / D]  (no reference counterpart; ARPACK starts from a random vector) */
+int rvgp_lift_guess(rvgp_handle_t h, const double* gauges, int64_t n, int D, int d, const double* U, int64_t ldu, int kL,
+                    double* out, int64_t ldo, int ncols);
+
 /* ---- K11/a15: frame contractions ------------------------------------------------------------------------
  * mode 0: out(n,d)   = G^T x      express_in_local_frame          (geometry.py:171-176)
  * mode 1: out(n,D)   = G x        express_in_local_frame(reverse) / eigenvector lift (dataclass.py:57-59)

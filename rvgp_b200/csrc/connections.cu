@@ -153,9 +153,35 @@ __global__ void frame_apply_kernel(const double* __restrict__ G, int64_t n, int 
     out[idx] = scale * s;
 }
 
+// Initial block for the Lc eigensolver from the scalar-Laplacian eigenvectors: smooth vector fields ~ (smooth scalar
+// function) x (constant ambient direction projected on the tangent frame):
+//   out[(i*d+q), c] = gauges[i][a][q] * U[i][j],   j = c / D, a = c % D
+__global__ void lift_guess_kernel(const double* __restrict__ G, int64_t n, int D, int d, const double* __restrict__ U, int64_t ldu,
+                                  int kL, double* __restrict__ out, int64_t ldo, int ncols) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * d * ncols) return;
+    const int c = (int)(idx % ncols);
+    const int64_t row = idx / ncols;
+    const int64_t i = row / d;
+    const int q = (int)(row % d);
+    const int j = c / D, a = c % D;
+    out[row * ldo + c] = (j < kL) ? __ldg(G + (i * D + a) * d + q) * __ldg(U + i * ldu + j) : 0.0;
+}
+
 }  // namespace rvgp
 
 using namespace rvgp;
+
+extern "C" int rvgp_lift_guess(rvgp_handle_t hh, const double* gauges, int64_t n, int D, int d, const double* U, int64_t ldu,
+                               int kL, double* out, int64_t ldo, int ncols) {
+    Handle* h = H(hh);
+    RVGP_REQUIRE(h, ncols >= 0 && ncols <= kL * D, "lift_guess: ncols must be <= kL * D");
+    const int64_t tot = n * d * ncols;
+    if (tot == 0) return RVGP_OK;
+    lift_guess_kernel<<<cdiv(tot, 256), 256, 0, h->stream>>>(gauges, n, D, d, U, ldu, kL, out, ldo, ncols);
+    RVGP_LAUNCH_OK(h, "lift_guess_kernel");
+    return RVGP_OK;
+}
 
 extern "C" int rvgp_connections(rvgp_handle_t hh, const double* gauges, int n, int D, int d, const int32_t* indptr,
                                 const int32_t* indices, int64_t nnzb, double* Lc_vals, double* R_vals) {

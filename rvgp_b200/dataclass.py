@@ -61,7 +61,8 @@ class data:
                  device=None,
                  eig_tol=1e-12,
                  verbose=True,
-                 shard=None):
+                 shard=None,
+                 warm_start=True):
         say = print if verbose else (lambda *a, **k: None)
         self._duals = {}
         self.timings = {}
@@ -163,7 +164,16 @@ class data:
             U_L_p = comm.allgather_rows(U_loc, counts)
             self.timings["eig_L"] = tick() - t0
             t0 = tick()
-            evals_Lc, U_loc = smallest_eigenpairs(S_Lc, k_Lc, upper_bound=hi, tol=eig_tol, stats=st_Lc, comm=comm)
+            r0, r1 = plan.r0, plan.r1
+
+            def lc_guess_loc(V, U=U_L_p[r0:r1], G=gauges_p[r0:r1].contiguous()):
+                hh = geo.get_handle(dev.index)
+                ncols = min(V.shape[1], U.shape[1] * D)
+                hh.call("rvgp_lift_guess", G, geo.I64(r1 - r0), int(D), int(dim_man), U, geo.I64(U.stride(0)),
+                        int(U.shape[1]), V, geo.I64(V.stride(0)), int(ncols))
+
+            evals_Lc, U_loc = smallest_eigenpairs(S_Lc, k_Lc, upper_bound=hi, tol=eig_tol, stats=st_Lc, comm=comm,
+                                                  init_fn=lc_guess_loc if warm_start else None)
             U_Lc_p = comm.allgather_rows(U_loc, [c * dim_man for c in counts])
             del U_loc
             self.timings["eig_Lc"] = tick() - t0
@@ -171,7 +181,15 @@ class data:
             evals_L, U_L_p = smallest_eigenpairs(A_L, k_L, upper_bound=hi, tol=eig_tol, stats=st_L)
             self.timings["eig_L"] = tick() - t0
             t0 = tick()
-            evals_Lc, U_Lc_p = smallest_eigenpairs(A_Lc, k_Lc, upper_bound=hi, tol=eig_tol, stats=st_Lc)
+            def lc_guess(V, U=U_L_p):
+                # smooth vector fields ~ scalar eigenfunctions x projected constant ambient directions
+                hh = geo.get_handle(dev.index)
+                ncols = min(V.shape[1], U.shape[1] * D)
+                hh.call("rvgp_lift_guess", gauges_p, geo.I64(n), int(D), int(dim_man), U, geo.I64(U.stride(0)),
+                        int(U.shape[1]), V, geo.I64(V.stride(0)), int(ncols))
+
+            evals_Lc, U_Lc_p = smallest_eigenpairs(A_Lc, k_Lc, upper_bound=hi, tol=eig_tol, stats=st_Lc,
+                                                   init_fn=lc_guess if warm_start else None)
             self.timings["eig_Lc"] = tick() - t0
         self.stats["eig_L"], self.stats["eig_Lc"] = st_L, st_Lc
 

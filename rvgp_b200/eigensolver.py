@@ -247,7 +247,7 @@ class _Dense:
 
 def smallest_eigenpairs(A, k, upper_bound, lower_bound=0.0, tol=1e-12, nex=None, seed=0, max_outer=80,
                         cond_max=1e6, deg0=20, panel=None, stats=None, verbose=False, comm=None,
-                        refine_bound=True):
+                        refine_bound=True, init_fn=None):
     """Smallest k eigenpairs of the symmetric PSD BsrMatrix ``A``.
 
     upper_bound: a rigorous upper bound of the spectrum (2 * max degree for (connection) Laplacians).
@@ -299,6 +299,8 @@ def smallest_eigenpairs(A, k, upper_bound, lower_bound=0.0, tol=1e-12, nex=None,
 
     V, W = B1, B2
     h.call("rvgp_fill_uniform_f64", I64(N), int(m), V, I64(V.stride(0)), U64(seed), I64(0), I64(A.row_offset))
+    if init_fn is not None:
+        init_fn(V)            # overwrite (some of) the random columns with an informed guess of the invariant subspace
 
     deg = np.full(m, deg0, dtype=np.int64)
     a_cut = lo_spec + 0.3 * (hi - lo_spec)

@@ -22,8 +22,8 @@ for b in (32, 64):
     for rot in (False,):
         A.d_code = A.d
         if rot: A.compress_rot2()
-        for stage in (0, 1):
-            h.set_option("spmm_remap", stage)
+        for stage in (0,):
+            pass
             for lpr in (0,):
                 h.set_option("spmm_lpr", lpr)
                 t = bench(A, X, W, Y1 if (stage or rot) else Y0)

@@ -199,3 +199,18 @@ def test_knn_grid_bit_identical_to_brute(kind, n, D):
         assert torch.equal(a, b) and torch.equal(ad, bd)
     part = geo.knn_device(Xd, 10, q_begin=1000, q_count=777, method="grid")
     assert torch.equal(part, geo.knn_device(Xd, 10, method="brute")[1000:1777])
+
+
+def test_full_decomposition_when_n_eigenpairs_is_none():
+    """n_eigenpairs=None -> k = N (geometry.py:68-71): the block solver degenerates to one exact Rayleigh-Ritz."""
+    from rvgp_b200.dataclass import data
+    from tests.workloads import make_cloud
+    X = make_cloud("sphere", 300, 3)
+    d = data(X, verbose=False)
+    assert d.evecs_L.shape == (300, 300) and d.evecs_Lc.shape == (900, 600)
+    ev = np.linalg.eigvalsh(d.Lc.toarray())
+    np.testing.assert_allclose(d.evals_Lc, ev, rtol=1e-9, atol=1e-10)
+    evL = np.linalg.eigvalsh(d.L.toarray())
+    np.testing.assert_allclose(d.evals_L, evL, rtol=1e-9, atol=1e-10)
+    d2 = data(X, n_eigenpairs=250, verbose=False)            # k close to N
+    np.testing.assert_allclose(d2.evals_L, evL[:250], rtol=1e-8, atol=1e-9)

@@ -12,6 +12,9 @@
 // neighbour gathers of the 64 consecutive block rows of a CTA hit L1/L2.
 #include "common.cuh"
 
+#ifndef RVGP_V2_NT
+#define RVGP_V2_NT 256
+#endif
 #ifndef RVGP_SPMM_STREAMING
 #define RVGP_SPMM_STREAMING 1
 #endif
@@ -118,7 +121,7 @@ bsr_spmm_kernel(int nbrows, const int* __restrict__ indptr, const int* __restric
 // loads were ~40 % of the pipe work.  With STAGE the CTA first copies the (contiguous) values and column indices of its 64
 // block rows into shared memory with coalesced loads; the inner loop then reads them with broadcast LDS (one wavefront).
 template <int D, int LPR, int CPL2, int U, bool PATTERN, bool ROT2, bool STAGE, bool ROWLIST>
-__global__ void __launch_bounds__(256, (D == 2 && CPL2 == 1 && !PATTERN && !ROT2 && !STAGE && !ROWLIST) ? 6 : 1)   // 40 regs, 48 warps/SM: +5 % (measured)
+__global__ void __launch_bounds__(RVGP_V2_NT, (RVGP_V2_NT == 256 && D == 2 && CPL2 == 1 && !PATTERN && !ROT2 && !STAGE && !ROWLIST) ? 6 : 1)   // 40 regs, 48 warps/SM: +5 % (measured)
 bsr_spmm_v2_kernel(int nbrows, const int* __restrict__ indptr, const int* __restrict__ indices,
                    const double* __restrict__ vals, const double* __restrict__ X, int64_t ldx,
                    const double* __restrict__ W, int64_t ldw, double* __restrict__ Y, int64_t ldy,
@@ -128,7 +131,7 @@ bsr_spmm_v2_kernel(int nbrows, const int* __restrict__ indptr, const int* __rest
     constexpr int VB = ROT2 ? 2 : D * D;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane / LPR, l = lane % LPR;
-    const int rows_per_cta = 8 * GPW * rows_per_group;
+    const int rows_per_cta = (RVGP_V2_NT / 32) * GPW * rows_per_group;
     const int row0 = blockIdx.x * rows_per_cta;
     const int npairs = ncols >> 1;
     extern __shared__ __align__(16) double stage_smem[];
@@ -143,8 +146,8 @@ bsr_spmm_v2_kernel(int nbrows, const int* __restrict__ indptr, const int* __rest
         staged = ne <= stage_cap;
         if (staged) {
             const double* vsrc = vals + (int64_t)te0 * VB;
-            for (int t = threadIdx.x; t < ne * VB; t += 256) svals[t] = __ldg(vsrc + t);
-            for (int t = threadIdx.x; t < ne; t += 256) sidx[t] = __ldg(indices + te0 + t);
+            for (int t = threadIdx.x; t < ne * VB; t += RVGP_V2_NT) svals[t] = __ldg(vsrc + t);
+            for (int t = threadIdx.x; t < ne; t += RVGP_V2_NT) sidx[t] = __ldg(indices + te0 + t);
         }
         __syncthreads();
     }
@@ -153,7 +156,7 @@ bsr_spmm_v2_kernel(int nbrows, const int* __restrict__ indptr, const int* __rest
     for (int cc = 0; cc < CPL2; ++cc) colok[cc] = (l + LPR * cc) < npairs;
 
     for (int it = 0; it < rows_per_group; ++it) {
-        const int vi = row0 + it * (8 * GPW) + warp * GPW + g;
+        const int vi = row0 + it * ((RVGP_V2_NT / 32) * GPW) + warp * GPW + g;
         if (vi >= (ROWLIST ? nlist : nbrows)) continue;
         const int i = ROWLIST ? __ldg(rowlist + vi) : vi;      // optional row list (boundary rows of a row-sharded matrix)
         const int e0 = __ldg(indptr + i), e1 = __ldg(indptr + i + 1);
@@ -272,10 +275,10 @@ static int launch_spmm_v2(Handle* h, int nbrows, const int* indptr, const int* i
 #define RVGP_V2(LPR, CPL2)                                                                                 \
     do {                                                                                                   \
         constexpr int U = (D * CPL2 <= 2) ? 4 : ((D * CPL2 <= 4) ? 2 : 1);                                 \
-        const int rows_per_cta = 8 * (32 / LPR) * rpg;                                                     \
+        const int rows_per_cta = (RVGP_V2_NT / 32) * (32 / LPR) * rpg;                                                     \
         const int grid_ = cdiv(h->rowlist ? h->nlist : nbrows, rows_per_cta);                              \
         if (h->rowlist) {                                                                                  \
-            bsr_spmm_v2_kernel<D, LPR, CPL2, U, PATTERN, ROT2, false, true><<<grid_, 256, 0, h->stream>>>( \
+            bsr_spmm_v2_kernel<D, LPR, CPL2, U, PATTERN, ROT2, false, true><<<grid_, RVGP_V2_NT, 0, h->stream>>>( \
                 nbrows, indptr, indices, vals, X, ldx, W, ldw, Y, ldy, ncols, alpha, beta, gamma, rpg, 0, h->rowlist, h->nlist); \
         } else if (!PATTERN && h->spmm_stage) {                                                            \
             constexpr int VB_ = ROT2 ? 2 : D * D;                                                          \
@@ -283,10 +286,10 @@ static int launch_spmm_v2(Handle* h, int nbrows, const int* indptr, const int* i
             const int smem = cap * (VB_ * 8 + 4);                                                          \
             auto kern = bsr_spmm_v2_kernel<D, LPR, CPL2, U, PATTERN, ROT2, true, false>;                   \
             if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
-            kern<<<grid_, 256, smem, h->stream>>>(                                                         \
+            kern<<<grid_, RVGP_V2_NT, smem, h->stream>>>(                                                         \
                 nbrows, indptr, indices, vals, X, ldx, W, ldw, Y, ldy, ncols, alpha, beta, gamma, rpg, cap, nullptr, 0); \
         } else {                                                                                           \
-            bsr_spmm_v2_kernel<D, LPR, CPL2, U, PATTERN, ROT2, false, false><<<grid_, 256, 0, h->stream>>>( \
+            bsr_spmm_v2_kernel<D, LPR, CPL2, U, PATTERN, ROT2, false, false><<<grid_, RVGP_V2_NT, 0, h->stream>>>( \
                 nbrows, indptr, indices, vals, X, ldx, W, ldw, Y, ldy, ncols, alpha, beta, gamma, rpg, 0, nullptr, 0); \
         }                                                                                                  \
     } while (0)

@@ -112,6 +112,33 @@ int rvgp_cheb_filter_merged_f64(rvgp_handle_t h, int nbrows, int d, int R, const
                                 double* work0, double* work1, int64_t ldw, int ncols, int degree, double lo_spec,
                                 double lo_cut, double hi);
 
+/* ---- K9 v4: row-group SpMM on the FP64 tensor path (mma.sync.m8n8k4.f64), d in {1, 2}.  Groups of 8/d consecutive
+ * block rows are the 8 MMA rows; the union of their column lists (rvgp_bsr_merge_plan with R = 8/d) is cut into k-steps of
+ * 4/d columns.  rvgp_bsr_mma_pack writes, per k-step, the column indices (kcols) and the dense 8x4 slice of A in
+ * fragment order (afrag, 32 doubles, zero where a row does not store the column); kptr (ngroups+1) is the exclusive
+ * prefix of the k-steps per group, computed by the caller from gptr.  vals == NULL (d == 1) packs the unit-weight graph
+ * Laplacian.  rvgp_bsr_spmm_mma_f64 has the contract of rvgp_bsr_spmm_f64; it needs ncols % 16 == 0, 32-byte aligned
+ * X / W / Y and leading dimensions % 4 == 0.  rvgp_cheb_filter_mma_f64 = rvgp_cheb_filter_f64 on top of it. */
+int rvgp_bsr_mma_pack(rvgp_handle_t h, int nbrows, int d, const int32_t* indptr, const int32_t* indices,
+                      const double* vals, const int32_t* gptr, const int32_t* uent, const int32_t* kptr, int32_t* kcols,
+                      double* afrag);
+int rvgp_bsr_spmm_mma_f64(rvgp_handle_t h, int nbrows, int d, const int32_t* kptr, const int32_t* kcols,
+                          const double* afrag, const double* X, int64_t ldx, const double* W, int64_t ldw, double* Y,
+                          int64_t ldy, int ncols, double alpha, double beta, double gamma);
+/* node-contiguous panels (d == 2): element (2*node+q, 2*cp+e) at Xn[node*ns + (cp*2+q)*2 + e]; beta is folded into the
+ * diagonal as beta/alpha (alpha != 0).  rvgp_bsr_mma_rotc compacts the plan when every block is a scaled rotation /
+ * reflection (16 doubles + sign bits per k-step; bad_flag != 0: not applicable, re-pack kcols); pass rotc = 1 then.
+ * reverse != 0 walks the row groups backwards (alternate between the steps of a recurrence for L2 reuse). */
+int rvgp_bsr_spmm_mma_native_f64(rvgp_handle_t h, int nbrows, const int32_t* kptr, const int32_t* kcols,
+                                 const double* afrag, int rotc, const double* Xn, int64_t nsx, const double* Wn,
+                                 int64_t nsw, double* Yn, int64_t nsy, int ncols, double alpha, double beta, double gamma,
+                                 int reverse);
+int rvgp_bsr_mma_rotc(rvgp_handle_t h, int64_t nk, const double* afrag, int32_t* kcols, double* afrag_c,
+                      int32_t* bad_flag, double rtol);
+int rvgp_cheb_filter_mma_f64(rvgp_handle_t h, int nbrows, int d, const int32_t* kptr, const int32_t* kcols,
+                             const double* afrag, double* V, int64_t ldv, double* work0, double* work1, int64_t ldw,
+                             int ncols, int degree, double lo_spec, double lo_cut, double hi);
+
 /* ---- K10: dense FP64 kernels for orthogonalisation / Rayleigh-Ritz ---------------------------------
  * C (m x n, ldc) = alpha * op(A) * op(B).  Layout flags say which index of each operand is contiguous:
  *   a_kmajor = 0: A(i,k) = A[k*lda + i]  ("A is stored as K x M", e.g. V^T of a tall block vector)

@@ -21,6 +21,10 @@ struct Handle {
     int nlist;
     int spmm_stage;               // tuning: stage block values / indices of a CTA's rows in shared memory
     int dgemm_dmma;               // tuning: FP64 tensor (mma.sync m8n8k4) instead of the DFMA register tile
+    int mma_gpw;                  // tuning: row groups per warp in the MMA SpMM (0 = default)
+    int mma_variant;              // tuning: pipeline / occupancy variant of the native-layout MMA SpMM
+    int mma_prefetch;             // tuning: L2 prefetch distance (warp iterations) of the native-layout MMA SpMM
+    int mma_stream_policy;        // tuning: bit0 = no-L1-allocate W loads, bit1 = no-L1-allocate Y stores (MMA SpMM)
 };
 
 inline Handle* H(rvgp_handle_t h) { return reinterpret_cast<Handle*>(h); }

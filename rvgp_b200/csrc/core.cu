@@ -20,6 +20,10 @@ extern "C" int rvgp_create(int device, rvgp_handle_t* out) {
     h->nlist = 0;
     h->spmm_stage = 0;   // measured: no gain (tools/profile_stage.py); value loads are not the limiter
     h->dgemm_dmma = 1;   // measured on B200: 17 vs 14 TFLOP/s for the tall-skinny Gram (tools/ncu_dgemm.py)
+    h->mma_gpw = 0;
+    h->mma_stream_policy = 0;
+    h->mma_variant = 0;
+    h->mma_prefetch = 1;
     h->last_error[0] = 0;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete h; return RVGP_ERR_CUDA; }
@@ -50,5 +54,9 @@ extern "C" int rvgp_set_option(rvgp_handle_t hh, const char* key, int value) {
     if (strcmp(key, "spmm_v1") == 0) { H(hh)->spmm_v1 = value; return RVGP_OK; }
     if (strcmp(key, "spmm_stage") == 0) { H(hh)->spmm_stage = value; return RVGP_OK; }
     if (strcmp(key, "dgemm_dmma") == 0) { H(hh)->dgemm_dmma = value; return RVGP_OK; }
+    if (strcmp(key, "mma_variant") == 0) { H(hh)->mma_variant = value; return RVGP_OK; }
+    if (strcmp(key, "mma_prefetch") == 0) { H(hh)->mma_prefetch = value; return RVGP_OK; }
+    if (strcmp(key, "mma_gpw") == 0) { H(hh)->mma_gpw = value; return RVGP_OK; }
+    if (strcmp(key, "mma_stream_policy") == 0) { H(hh)->mma_stream_policy = value; return RVGP_OK; }
     return set_error(H(hh), RVGP_ERR_BAD_ARG, "unknown option %s%s", key);
 }

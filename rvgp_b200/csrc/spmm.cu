@@ -534,6 +534,35 @@ extern "C" int rvgp_cheb_filter_merged_f64(rvgp_handle_t hh, int nbrows, int d, 
     return RVGP_OK;
 }
 
+namespace rvgp {
+int spmm_mma_dispatch(Handle* h, int nbrows, int d, const int* kptr, const int* kcols, const double* afrag,
+                      const double* X, int64_t ldx, const double* W, int64_t ldw, double* Y, int64_t ldy, int ncols,
+                      double alpha, double beta, double gamma);
+}
+
+// Same filter through the FP64-MMA row-group SpMM (rvgp_bsr_spmm_mma_f64, spmm_mma.cu).
+extern "C" int rvgp_cheb_filter_mma_f64(rvgp_handle_t hh, int nbrows, int d, const int32_t* kptr, const int32_t* kcols,
+                                        const double* afrag, double* V, int64_t ldv, double* work0, double* work1,
+                                        int64_t ldw, int ncols, int degree, double lo_spec, double lo_cut, double hi) {
+    Handle* h = H(hh);
+    RVGP_REQUIRE(h, degree >= 0, "cheb_filter: degree >= 0");
+    RVGP_REQUIRE(h, hi > lo_cut && lo_cut > lo_spec, "cheb_filter: need lo_spec < lo_cut < hi");
+    if (degree == 0 || nbrows == 0) return RVGP_OK;
+    double* buf[3] = {V, work0, work1};
+    int64_t ld[3] = {ldv, ldw, ldw};
+    int slot = 0;
+    auto apply = [&](const double* X, int64_t ldx, const double* W, int64_t ldw_, double* Y, int64_t ldy, double a, double b,
+                     double g) { return spmm_mma_dispatch(h, nbrows, d, kptr, kcols, afrag, X, ldx, W, ldw_, Y, ldy, ncols, a, b, g); };
+    int rc = cheb_recurrence(h, apply, (int64_t)nbrows * d, buf, ld, ncols, degree, lo_spec, lo_cut, hi, &slot);
+    if (rc) return rc;
+    if (slot != 0) {
+        RVGP_CUDA_OK(h, cudaMemcpy2DAsync(V, ldv * sizeof(double), buf[slot], ld[slot] * sizeof(double),
+                                          (size_t)ncols * sizeof(double), (size_t)nbrows * d, cudaMemcpyDeviceToDevice,
+                                          h->stream));
+    }
+    return RVGP_OK;
+}
+
 // Same filter through the shared-memory-staged SpMM (rvgp_bsr_spmm_tiled_f64).  The panel is first copied into a
 // CONTIGUOUS scratch panel so that every staged neighbour is one bulk copy of d*ncols*8 bytes; work0..work2 are three
 // (nrows x ncols) contiguous scratch panels.

@@ -61,6 +61,12 @@ class BsrMatrix:
             dc, ix, vl = self.d_code, self.indices_k, self.vals_k
         else:
             dc, ix, vl = self.d, self.indices, self.vals
+        if self._mma_ok(ncols, X, Y, W):
+            mp = self.mma
+            h.call("rvgp_bsr_spmm_mma_f64", self.nbrows, self.d, mp["kptr"], mp["kcols"], mp["afrag"],
+                   X, I64(X.stride(0)), W, I64(W.stride(0) if W is not None else 0), Y, I64(Y.stride(0)),
+                   int(ncols), float(alpha), float(beta), float(gamma))
+            return Y
         if self._merged_ok(ncols, X, Y, W):
             mp = self.merged
             h.call("rvgp_bsr_spmm_merged_f64", self.nbrows, dc, mp["R"], self.indptr, ix, mp["gptr"], mp["uent"], vl,
@@ -71,6 +77,43 @@ class BsrMatrix:
                X, I64(X.stride(0)), W, I64(W.stride(0) if W is not None else 0), Y, I64(Y.stride(0)),
                int(ncols), float(alpha), float(beta), float(gamma))
         return Y
+
+    # ---- FP64-MMA row-group variant (K9 v4, spmm_mma.cu) ----------------------------------------------------
+    mma = None
+
+    def build_mma_plan(self, h=None):
+        """k-step plan of rvgp_bsr_spmm_mma_f64: groups of 8/d block rows x k-steps of 4/d union columns."""
+        if self.d not in (1, 2) or self.nbrows == 0:
+            return None
+        if getattr(self, "_mma_plan", None) is not None:
+            return self._mma_plan
+        h = h or get_handle(self.indptr.device.index)
+        dev = self.indptr.device
+        R, T = 8 // self.d, 4 // self.d
+        mp = self.build_merge_plan(R, h=h)
+        gptr = mp["gptr"]
+        ns = (gptr[1:] - gptr[:-1] + (T - 1)) // T
+        kptr = torch.zeros(gptr.numel(), dtype=torch.int32, device=dev)
+        kptr[1:] = torch.cumsum(ns, 0).to(torch.int32)
+        nk = int(kptr[-1].item())
+        kcols = torch.empty(max(1, nk * T), dtype=torch.int32, device=dev)
+        afrag = torch.empty(max(1, nk * 32), dtype=torch.float64, device=dev)
+        h.call("rvgp_bsr_mma_pack", self.nbrows, self.d, self.indptr, self.indices, self.vals, gptr, mp["uent"], kptr,
+               kcols, afrag)
+        self._mma_plan = dict(kptr=kptr, kcols=kcols, afrag=afrag, ksteps=nk, reuse=mp["reuse"],
+                              fill=self.nnzb / max(1, nk * R * T))
+        self.__dict__.get("_mplans", {}).pop(R, None)      # the union lists are only needed for packing
+        return self._mma_plan
+
+    def enable_mma(self, on=True, h=None):
+        """Route spmm / cheb_filter through the FP64-MMA kernel whenever shapes / alignment allow it."""
+        self.mma = self.build_mma_plan(h=h) if on else None
+        return self.mma
+
+    def _mma_ok(self, ncols, *tensors):
+        if self.mma is None or ncols % 16:
+            return False
+        return all(t is None or (t.stride(0) % 4 == 0 and t.data_ptr() % 32 == 0) for t in tensors)
 
     # ---- row-group merged variant (K9 v3) -------------------------------------------------------------------
     def build_merge_plan(self, R=4, h=None):
@@ -163,6 +206,12 @@ class BsrMatrix:
             dc, ix, vl = self.d_code, self.indices_k, self.vals_k
         else:
             dc, ix, vl = self.d, self.indices, self.vals
+        if self._mma_ok(ncols, Vp, w0, w1):
+            mp = self.mma
+            h.call("rvgp_cheb_filter_mma_f64", self.nbrows, self.d, mp["kptr"], mp["kcols"], mp["afrag"],
+                   Vp, I64(Vp.stride(0)), w0, w1, I64(w0.stride(0)), int(ncols), int(degree), float(lo_spec),
+                   float(lo_cut), float(hi))
+            return
         if self._merged_ok(ncols, Vp, w0, w1):
             mp = self.merged
             h.call("rvgp_cheb_filter_merged_f64", self.nbrows, dc, mp["R"], self.indptr, ix, mp["gptr"], mp["uent"], vl,

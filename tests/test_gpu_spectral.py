@@ -248,3 +248,55 @@ def test_spmm_merged_matches_scipy(case, ncols, R):
             A.spmm(Xd, Yd, alpha=0.7, beta=-1.3, gamma=0.25, W=Wd)
             ref2 = 0.7 * ref - 1.3 * X + 0.25 * W
             assert np.abs(Yd.cpu().numpy() - ref2).max() <= 1e-13 * max(1.0, np.abs(ref2).max())
+
+
+@pytest.mark.parametrize("case", ["sphere_n2000_k50", "flat3torus_R6_n900_k24", "torus_n600_k20"])
+@pytest.mark.parametrize("ncols", [16, 32, 48, 64, 128])
+def test_spmm_mma_matches_scipy(case, ncols):
+    """K9 v4 (FP64 mma.sync row-group SpMM) == SciPy for the d = 2 connection Laplacian and the pattern-mode L,
+    on contiguous blocks and on column panels of a wider block vector; shapes the MMA path cannot take fall back."""
+    g = load_golden(case)
+    for which in ("Lc", "L"):
+        A, S = _bsr_from_golden(g, which)
+        if A.d not in (1, 2):
+            assert A.enable_mma() is None
+            continue
+        mp = A.enable_mma()
+        assert mp["ksteps"] > 0 and 0.0 < mp["fill"] <= 1.0
+        rng = np.random.default_rng(5)
+        X = rng.normal(size=(A.nrows, ncols)); W = rng.normal(size=(A.nrows, ncols))
+        big = torch.zeros((A.nrows, ncols + 32), dtype=torch.float64, device=_dev())
+        big[:, 16:16 + ncols] = torch.from_numpy(X).to(_dev())
+        Wd = torch.from_numpy(W).to(_dev())
+        for Xd in (torch.from_numpy(X).to(_dev()), big[:, 16:16 + ncols]):
+            assert A._mma_ok(ncols, Xd, Wd)
+            Yd = torch.full((A.nrows, ncols), 7.0, dtype=torch.float64, device=_dev())
+            A.spmm(Xd, Yd)
+            ref = S @ X
+            assert np.abs(Yd.cpu().numpy() - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max())
+            A.spmm(Xd, Yd, alpha=0.7, beta=-1.3, gamma=0.25, W=Wd)
+            ref2 = 0.7 * ref - 1.3 * X + 0.25 * W
+            assert np.abs(Yd.cpu().numpy() - ref2).max() <= 1e-13 * max(1.0, np.abs(ref2).max())
+        # unaligned panel / odd width: falls back to the gather kernel, same answer
+        Xo = big[:, 3:3 + 10]
+        assert not A._mma_ok(10, Xo)
+        Yo = torch.empty((A.nrows, 10), dtype=torch.float64, device=_dev())
+        A.spmm(Xo, Yo)
+        assert np.abs(Yo.cpu().numpy() - S @ big[:, 3:13].cpu().numpy()).max() <= 1e-12
+
+
+@pytest.mark.parametrize("degree", [1, 2, 9])
+def test_cheb_filter_mma_matches_gather(degree):
+    g = load_golden("sphere_n2000_k50")
+    for which in ("Lc", "L"):
+        A, _ = _bsr_from_golden(g, which)
+        V0 = torch.from_numpy(np.random.default_rng(2).normal(size=(A.nrows, 96))).to(_dev())
+        outs = []
+        for on in (False, True):
+            A.enable_mma(on)
+            V = V0.clone()
+            w0 = torch.empty((A.nrows, 32), dtype=torch.float64, device=_dev()); w1 = torch.empty_like(w0)
+            A.cheb_filter(V[:, 32:64], w0, w1, 32, degree, 0.0, 3.0, 40.0)
+            outs.append(V.cpu().numpy())
+        assert np.abs(outs[0][:, :32] - V0[:, :32].cpu().numpy()).max() == 0.0
+        assert np.abs(outs[0] - outs[1]).max() <= 1e-12 * np.abs(outs[0]).max()

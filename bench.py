@@ -171,9 +171,13 @@ def run_b200(args):
     if os.path.exists(tp):
         try:
             traffic = json.load(open(tp)).get(wl)
+            if isinstance(traffic, dict):
+                traffic = traffic.get(st.get("spmm_kernel", "gather"))
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "bsr_spmm_v2_kernel (fused Chebyshev step, d=%d, %d columns)" % (A.d, panel),
+    kname = ("bsr_spmm_mma_native_kernel (FP64 mma.sync row-group SpMM, node-contiguous panels; fused Chebyshev step, d=%d, %d columns)"
+             if st.get("spmm_kernel") == "mma_native" else "bsr_spmm_v2_kernel (fused Chebyshev step, d=%d, %d columns)") % (A.d, panel)
+    roofline = {"bound": "hbm", "kernel": kname,
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "traffic": traffic, "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback",
                 "algorithmic_bytes_per_launch": int(bytes_fused), "avg_launch_ms": round(t_launch * 1e3, 4),

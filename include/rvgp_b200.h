@@ -135,9 +135,13 @@ int rvgp_bsr_spmm_mma_native_f64(rvgp_handle_t h, int nbrows, const int32_t* kpt
                                  int reverse);
 int rvgp_bsr_mma_rotc(rvgp_handle_t h, int64_t nk, const double* afrag, int32_t* kcols, double* afrag_c,
                       int32_t* bad_flag, double rtol);
+int rvgp_panel_native_f64(rvgp_handle_t h, int to_native, int nbrows, int ncols, double* V, int64_t ldv, double* Xn,
+                          int64_t ns);
+/* d == 2 and work2 != NULL: the recurrence runs on node-contiguous panels (work0..2 contiguous, ldw == ncols), V is
+ * converted on entry / exit; otherwise the row-major MMA kernel is used and work2 / rotc must be NULL / 0. */
 int rvgp_cheb_filter_mma_f64(rvgp_handle_t h, int nbrows, int d, const int32_t* kptr, const int32_t* kcols,
-                             const double* afrag, double* V, int64_t ldv, double* work0, double* work1, int64_t ldw,
-                             int ncols, int degree, double lo_spec, double lo_cut, double hi);
+                             const double* afrag, int rotc, double* V, int64_t ldv, double* work0, double* work1,
+                             double* work2, int64_t ldw, int ncols, int degree, double lo_spec, double lo_cut, double hi);
 
 /* ---- K10: dense FP64 kernels for orthogonalisation / Rayleigh-Ritz ---------------------------------
  * C (m x n, ldc) = alpha * op(A) * op(B).  Layout flags say which index of each operand is contiguous:

@@ -21,8 +21,10 @@ extern "C" int rvgp_create(int device, rvgp_handle_t* out) {
     h->spmm_stage = 0;   // measured: no gain (tools/profile_stage.py); value loads are not the limiter
     h->dgemm_dmma = 1;   // measured on B200: 17 vs 14 TFLOP/s for the tall-skinny Gram (tools/ncu_dgemm.py)
     h->mma_gpw = 0;
-    h->mma_stream_policy = 0;
-    h->mma_variant = 0;
+    // measured on B200 at C4 size (tools/profile_mma.py, profiles/r01_spmm_mma_sweep.txt): 256-thread CTAs x 2, register ring
+    // of 2 k-steps, persistent warp-strided schedule, streams evict-first in L2, L2 prefetch one group ahead
+    h->mma_stream_policy = 7;
+    h->mma_variant = 1;
     h->mma_prefetch = 1;
     h->last_error[0] = 0;
     cudaDeviceProp prop;

@@ -538,19 +538,44 @@ namespace rvgp {
 int spmm_mma_dispatch(Handle* h, int nbrows, int d, const int* kptr, const int* kcols, const double* afrag,
                       const double* X, int64_t ldx, const double* W, int64_t ldw, double* Y, int64_t ldy, int ncols,
                       double alpha, double beta, double gamma);
+int spmm_mma_native_dispatch(Handle* h, int nbrows, const int* kptr, const int* kcols, const double* afrag, int rotc,
+                             const double* X, int64_t nsx, const double* W, int64_t nsw, double* Y, int64_t nsy,
+                             int ncols, double alpha, double beta, double gamma, int reverse);
+int native_convert(Handle* h, bool to_native, int nbrows, int ncols, double* V, int64_t ldv, double* Xn, int64_t ns);
 }
 
-// Same filter through the FP64-MMA row-group SpMM (rvgp_bsr_spmm_mma_f64, spmm_mma.cu).
+// Same filter through the FP64-MMA row-group SpMM (spmm_mma.cu).
+//   d == 2 and work2 != NULL: the recurrence runs on NODE-CONTIGUOUS panels (rvgp_bsr_spmm_mma_native_f64): V is converted
+//     into work0, the three (nrows x ncols, contiguous) work panels rotate, the result is converted back into V.
+//     rotc != 0: kcols / afrag are the compact plan of rvgp_bsr_mma_rotc.
+//   otherwise: row-major kernel (rvgp_bsr_spmm_mma_f64), work2 unused.
 extern "C" int rvgp_cheb_filter_mma_f64(rvgp_handle_t hh, int nbrows, int d, const int32_t* kptr, const int32_t* kcols,
-                                        const double* afrag, double* V, int64_t ldv, double* work0, double* work1,
-                                        int64_t ldw, int ncols, int degree, double lo_spec, double lo_cut, double hi) {
+                                        const double* afrag, int rotc, double* V, int64_t ldv, double* work0, double* work1,
+                                        double* work2, int64_t ldw, int ncols, int degree, double lo_spec, double lo_cut,
+                                        double hi) {
     Handle* h = H(hh);
     RVGP_REQUIRE(h, degree >= 0, "cheb_filter: degree >= 0");
     RVGP_REQUIRE(h, hi > lo_cut && lo_cut > lo_spec, "cheb_filter: need lo_spec < lo_cut < hi");
     if (degree == 0 || nbrows == 0) return RVGP_OK;
+    int slot = 0;
+    if (d == 2 && work2 != nullptr) {
+        RVGP_REQUIRE(h, ldw == ncols, "cheb_filter_mma: the native path needs contiguous work panels (ldw == ncols)");
+        const int64_t ns = 2 * (int64_t)ncols;
+        int rc = native_convert(h, true, nbrows, ncols, V, ldv, work0, ns);
+        if (rc) return rc;
+        double* buf[3] = {work0, work1, work2};
+        int64_t ld[3] = {ns, ns, ns};
+        auto apply = [&](const double* X, int64_t nsx, const double* W, int64_t nsw, double* Y, int64_t nsy, double a, double b,
+                         double g) {
+            return spmm_mma_native_dispatch(h, nbrows, kptr, kcols, afrag, rotc, X, nsx, W, nsw, Y, nsy, ncols, a, b, g, 0);
+        };
+        rc = cheb_recurrence(h, apply, (int64_t)nbrows * d, buf, ld, ncols, degree, lo_spec, lo_cut, hi, &slot);
+        if (rc) return rc;
+        return native_convert(h, false, nbrows, ncols, V, ldv, buf[slot], ns);
+    }
+    RVGP_REQUIRE(h, rotc == 0, "cheb_filter_mma: the compact plan needs the native path (d == 2, work2 != NULL)");
     double* buf[3] = {V, work0, work1};
     int64_t ld[3] = {ldv, ldw, ldw};
-    int slot = 0;
     auto apply = [&](const double* X, int64_t ldx, const double* W, int64_t ldw_, double* Y, int64_t ldy, double a, double b,
                      double g) { return spmm_mma_dispatch(h, nbrows, d, kptr, kcols, afrag, X, ldx, W, ldw_, Y, ldy, ncols, a, b, g); };
     int rc = cheb_recurrence(h, apply, (int64_t)nbrows * d, buf, ld, ncols, degree, lo_spec, lo_cut, hi, &slot);

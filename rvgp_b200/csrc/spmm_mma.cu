@@ -423,6 +423,33 @@ __global__ void mma_rotc_kernel(int64_t nk, const double* __restrict__ afrag, in
     }
 }
 
+// Row-major panel (rows 2*node + q, leading dimension ldv) <-> node-contiguous panel (node stride ns).  One thread per
+// 16-byte unit (column pair cp, component q).
+template <bool TO_NATIVE>
+__global__ void native_convert_kernel(int64_t nbrows, int ncp, double* __restrict__ V, int64_t ldv, double* __restrict__ Xn,
+                                      int64_t ns) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t per_node = 2 * (int64_t)ncp;
+    if (idx >= nbrows * per_node) return;
+    const int64_t node = idx / per_node;
+    const int rem = (int)(idx - node * per_node);
+    const int q = rem / ncp, cp = rem - q * ncp;          // consecutive threads walk along a V row
+    double2* v = reinterpret_cast<double2*>(V + (2 * node + q) * ldv) + cp;
+    double2* x = reinterpret_cast<double2*>(Xn + node * ns) + (cp * 2 + q);
+    if (TO_NATIVE) *x = *v; else *v = *x;
+}
+
+int native_convert(Handle* h, bool to_native, int nbrows, int ncols, double* V, int64_t ldv, double* Xn, int64_t ns) {
+    RVGP_REQUIRE(h, ncols % 2 == 0 && ldv % 2 == 0 && ns % 2 == 0 && ns >= 2 * ncols && (uintptr_t)V % 16 == 0 &&
+                        (uintptr_t)Xn % 16 == 0, "native_convert: even ncols / strides and 16-byte aligned buffers");
+    if (nbrows == 0) return RVGP_OK;
+    const int64_t total = (int64_t)nbrows * ncols;
+    if (to_native) native_convert_kernel<true><<<cdiv(total, 256), 256, 0, h->stream>>>(nbrows, ncols / 2, V, ldv, Xn, ns);
+    else native_convert_kernel<false><<<cdiv(total, 256), 256, 0, h->stream>>>(nbrows, ncols / 2, V, ldv, Xn, ns);
+    RVGP_LAUNCH_OK(h, "native_convert_kernel");
+    return RVGP_OK;
+}
+
 int spmm_mma_native_dispatch(Handle* h, int nbrows, const int* kptr, const int* kcols, const double* afrag, int rotc,
                              const double* X, int64_t nsx, const double* W, int64_t nsw, double* Y, int64_t nsy,
                              int ncols, double alpha, double beta, double gamma, int reverse) {
@@ -437,7 +464,7 @@ int spmm_mma_native_dispatch(Handle* h, int nbrows, const int* kptr, const int* 
     const int ngroups = cdiv(nbrows, 4);
     const int gpw = h->mma_gpw;                       // 0 = persistent warp-strided schedule
     const int var = h->mma_variant;
-    const int nch = (ncols % 64 == 0 && var < 7) ? 4 : ((ncols % 32 == 0) ? 2 : 1);
+    const int nch = (ncols % 64 == 0) ? 4 : ((ncols % 32 == 0) ? 2 : 1);
     const int nslab = ncols / (16 * nch);
     const int has_w = gamma != 0.0;
     const double ascale = has_w ? alpha / gamma : 1.0, afold = has_w ? beta / gamma : beta / alpha, yscale = has_w ? gamma : alpha;
@@ -453,14 +480,13 @@ int spmm_mma_native_dispatch(Handle* h, int nbrows, const int* kptr, const int* 
             ngroups, nbrows, kptr, kcols, afrag, X, nsx, W, nsw, Y, nsy, ascale, afold, yscale, has_w, gpw, gpw <= 0,           \
             h->mma_prefetch, h->mma_stream_policy, reverse);                                                           \
     } while (0)
-    if (nch == 4) {                                   // (chunks, ring depth, threads, CTAs/SM)
-        if (var == 1) RVGP_MMAN(4, 2, 256, 2); else if (var == 2) RVGP_MMAN(4, 3, 128, 4); else if (var == 3) RVGP_MMAN(4, 3, 256, 2);
-        else if (var == 4) RVGP_MMAN(4, 2, 128, 5); else if (var == 5) RVGP_MMAN(4, 4, 128, 3); else if (var == 6) RVGP_MMAN(4, 3, 384, 1); else if (var == 11) RVGP_MMAN(4, 3, 512, 1); else if (var == 12) RVGP_MMAN(4, 3, 448, 1);
-        else if (var == 13) RVGP_MMAN(4, 4, 384, 1); else if (var == 14) RVGP_MMAN(4, 3, 192, 2);
-        else RVGP_MMAN(4, 2, 128, 4);
+    // (chunks of 16 columns, register-ring depth, threads per CTA, CTAs per SM); measured at C4 size, persistent schedule,
+    // policy 7 (profiles/r01_spmm_mma_sweep.txt): 1: 0.828 ms | 0: 0.854 | 6: 0.851 | 5: 0.858 | 3: 0.864 | 2: 0.882
+    if (nch == 4) {
+        if (var == 0) RVGP_MMAN(4, 2, 128, 4); else if (var == 2) RVGP_MMAN(4, 3, 128, 4); else if (var == 3) RVGP_MMAN(4, 3, 256, 2);
+        else if (var == 5) RVGP_MMAN(4, 4, 128, 3); else if (var == 6) RVGP_MMAN(4, 3, 384, 1); else RVGP_MMAN(4, 2, 256, 2);
     } else if (nch == 2) {
-        if (var == 7) RVGP_MMAN(2, 3, 128, 6); else if (var == 8) RVGP_MMAN(2, 4, 128, 5); else if (var == 9) RVGP_MMAN(2, 4, 256, 3);
-        else if (var == 10) RVGP_MMAN(2, 3, 256, 3); else RVGP_MMAN(2, 2, 128, 6);
+        RVGP_MMAN(2, 2, 128, 6);
     } else {
         RVGP_MMAN(1, 2, 128, 6);
     }
@@ -522,4 +548,11 @@ extern "C" int rvgp_bsr_mma_rotc(rvgp_handle_t hh, int64_t nk, const double* afr
     mma_rotc_kernel<<<cdiv(nk, 4), 128, 0, h->stream>>>(nk, afrag, kcols, afrag_c, bad_flag, rtol);
     RVGP_LAUNCH_OK(h, "mma_rotc_kernel");
     return RVGP_OK;
+}
+
+// Layout conversion between a row-major (2*nbrows x ncols, leading dimension ldv) panel and the node-contiguous panel
+// of rvgp_bsr_spmm_mma_native_f64 (node stride ns >= 2*ncols).  to_native != 0: V -> Xn, else Xn -> V.
+extern "C" int rvgp_panel_native_f64(rvgp_handle_t hh, int to_native, int nbrows, int ncols, double* V, int64_t ldv,
+                                     double* Xn, int64_t ns) {
+    return native_convert(H(hh), to_native != 0, nbrows, ncols, V, ldv, Xn, ns);
 }

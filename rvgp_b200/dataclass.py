@@ -9,6 +9,7 @@ from device-resident results on first access: building a 12 M-edge networkx grap
 eigenvector matrix to the host eagerly would cost more than the whole GPU pipeline.  Assigning to an attribute
 (examples overwrite ``d.vectors``, ``d.evals_Lc``, ``d.evecs_Lc``) replaces the value for every later consumer.
 """
+import os
 import time
 
 import numpy as np
@@ -141,6 +142,11 @@ class data:
         # ROT2 block storage (rvgp_bsr_compress_rot2) halves the matrix bytes but measured no faster (DESIGN.md K9 log)
         self.stats["rot2"] = False
         A_L = BsrMatrix(n, 1, p_indptr, p_indices, None)
+        # K9 v4: the Chebyshev filter of the d = 2 connection Laplacian runs on the FP64-MMA row-group kernel
+        # (0.65 vs 0.48 of HBM peak at C4 size; DESIGN.md K9 log).  RVGP_SPMM_MMA=0 keeps the gather kernel.
+        self.stats["spmm_mma"] = False
+        if dim_man == 2 and not shard and n >= 64 and os.environ.get("RVGP_SPMM_MMA", "1") != "0":
+            self.stats["spmm_mma"] = A_Lc.enable_mma() is not None
         self.timings["connections"] = tick() - t0
 
         say('Compute eigendecompositions')

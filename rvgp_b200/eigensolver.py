@@ -80,9 +80,12 @@ class BsrMatrix:
 
     # ---- FP64-MMA row-group variant (K9 v4, spmm_mma.cu) ----------------------------------------------------
     mma = None
+    mma_rowmajor = False      # experiment: also route single products / row-major filters through the (slower) row-major MMA kernel
 
-    def build_mma_plan(self, h=None):
-        """k-step plan of rvgp_bsr_spmm_mma_f64: groups of 8/d block rows x k-steps of 4/d union columns."""
+    def build_mma_plan(self, h=None, compact=True, keep_full=False):
+        """k-step plan of the MMA SpMM: groups of 8/d block rows x k-steps of 4/d union columns.  For d == 2 the
+        fragments are compacted to (a, b) + sign bits when every block is a scaled rotation / reflection (always true for
+        the connection Laplacian); ``keep_full`` keeps the 32-double fragments as well (row-major kernel)."""
         if self.d not in (1, 2) or self.nbrows == 0:
             return None
         if getattr(self, "_mma_plan", None) is not None:
@@ -100,20 +103,69 @@ class BsrMatrix:
         afrag = torch.empty(max(1, nk * 32), dtype=torch.float64, device=dev)
         h.call("rvgp_bsr_mma_pack", self.nbrows, self.d, self.indptr, self.indices, self.vals, gptr, mp["uent"], kptr,
                kcols, afrag)
-        self._mma_plan = dict(kptr=kptr, kcols=kcols, afrag=afrag, ksteps=nk, reuse=mp["reuse"],
-                              fill=self.nnzb / max(1, nk * R * T))
+        plan = dict(kptr=kptr, kcols=kcols, afrag=afrag, ksteps=nk, reuse=mp["reuse"],
+                    fill=self.nnzb / max(1, nk * R * T), rotc=0, kcols_c=None, afrag_c=None)
         self.__dict__.get("_mplans", {}).pop(R, None)      # the union lists are only needed for packing
-        return self._mma_plan
+        if compact and self.d == 2 and self.vals is not None and nk > 0:
+            kcols_c = kcols.clone()
+            afrag_c = torch.empty(nk * 16, dtype=torch.float64, device=dev)
+            bad = torch.zeros(1, dtype=torch.int32, device=dev)
+            h.call("rvgp_bsr_mma_rotc", I64(nk), afrag, kcols_c, afrag_c, bad, 1e-12)
+            if int(bad.item()) == 0:
+                plan.update(rotc=1, kcols_c=kcols_c, afrag_c=afrag_c)
+                if not keep_full:
+                    plan["afrag"] = None                   # C4: 0.86 GB
+        self._mma_plan = plan
+        return plan
 
-    def enable_mma(self, on=True, h=None):
-        """Route spmm / cheb_filter through the FP64-MMA kernel whenever shapes / alignment allow it."""
-        self.mma = self.build_mma_plan(h=h) if on else None
+    def enable_mma(self, on=True, h=None, rowmajor=False):
+        """Route cheb_filter (d == 2: node-contiguous panels) through the FP64-MMA kernel whenever shapes / alignment
+        allow it; ``rowmajor`` additionally routes single products through the row-major MMA kernel (experiment)."""
+        if on and rowmajor and getattr(self, "_mma_plan", None) is not None and self._mma_plan["afrag"] is None:
+            self._mma_plan = None
+        self.mma = self.build_mma_plan(h=h, keep_full=rowmajor) if on else None
+        self.mma_rowmajor = bool(on and rowmajor and self.mma is not None)
         return self.mma
 
     def _mma_ok(self, ncols, *tensors):
-        if self.mma is None or ncols % 16:
+        if self.mma is None or not self.mma_rowmajor or ncols % 16:
             return False
         return all(t is None or (t.stride(0) % 4 == 0 and t.data_ptr() % 32 == 0) for t in tensors)
+
+    def _mma_native_ok(self, ncols, Vp, w0, w1, w2):
+        if self.mma is None or self.d != 2 or w2 is None or ncols % 16:
+            return False
+        if Vp.stride(0) % 2 or Vp.data_ptr() % 16:
+            return False
+        return all(t.stride(0) == ncols and t.data_ptr() % 16 == 0 and t.shape[1] == ncols for t in (w0, w1, w2))
+
+    def to_native(self, X, out=None, h=None):
+        """Row-major (2 n x b) block -> node-contiguous (n x 2b) panel of the native MMA kernel."""
+        h = h or get_handle(X.device.index)
+        b = X.shape[1]
+        if out is None:
+            out = torch.empty((self.nbrows, 2 * b), dtype=torch.float64, device=X.device)
+        h.call("rvgp_panel_native_f64", 1, self.nbrows, int(b), X, I64(X.stride(0)), out, I64(out.stride(0)))
+        return out
+
+    def from_native(self, Xn, out=None, h=None):
+        h = h or get_handle(Xn.device.index)
+        b = Xn.shape[1] // 2
+        if out is None:
+            out = torch.empty((self.nrows, b), dtype=torch.float64, device=Xn.device)
+        h.call("rvgp_panel_native_f64", 0, self.nbrows, int(b), out, I64(out.stride(0)), Xn, I64(Xn.stride(0)))
+        return out
+
+    def spmm_native(self, Xn, Yn, alpha=1.0, beta=0.0, gamma=0.0, Wn=None, reverse=False, h=None):
+        """Y = alpha A X + beta X + gamma W on node-contiguous panels (d == 2, MMA plan enabled, alpha != 0)."""
+        h = h or get_handle(Xn.device.index)
+        mp = self.mma
+        rotc = mp["rotc"]
+        h.call("rvgp_bsr_spmm_mma_native_f64", self.nbrows, mp["kptr"], mp["kcols_c"] if rotc else mp["kcols"],
+               mp["afrag_c"] if rotc else mp["afrag"], int(rotc), Xn, I64(Xn.stride(0)), Wn,
+               I64(Wn.stride(0) if Wn is not None else 0), Yn, I64(Yn.stride(0)), int(Xn.shape[1] // 2), float(alpha),
+               float(beta), float(gamma), int(bool(reverse)))
+        return Yn
 
     # ---- row-group merged variant (K9 v3) -------------------------------------------------------------------
     def build_merge_plan(self, R=4, h=None):
@@ -197,19 +249,27 @@ class BsrMatrix:
 
     row_offset = 0          # global row of local row 0 (non-zero only for row-sharded operators)
 
-    def cheb_filter(self, Vp, w0, w1, ncols, degree, lo_spec, lo_cut, hi, h=None):
-        """Degree-`degree` Chebyshev filter of the panel Vp in place; the whole recurrence runs inside one C call."""
+    def cheb_filter(self, Vp, w0, w1, ncols, degree, lo_spec, lo_cut, hi, h=None, w2=None):
+        """Degree-`degree` Chebyshev filter of the panel Vp in place; the whole recurrence runs inside one C call.
+        With a third contiguous work panel ``w2`` and an MMA plan (d == 2) the recurrence runs on node-contiguous panels."""
         h = h or get_handle(Vp.device.index)
         aligned = (ncols % 2 == 0 and Vp.stride(0) % 2 == 0 and w0.stride(0) % 2 == 0 and Vp.data_ptr() % 16 == 0
                    and w0.data_ptr() % 16 == 0 and w1.data_ptr() % 16 == 0)
+        if self._mma_native_ok(ncols, Vp, w0, w1, w2):
+            mp = self.mma
+            rotc = mp["rotc"]
+            h.call("rvgp_cheb_filter_mma_f64", self.nbrows, self.d, mp["kptr"], mp["kcols_c"] if rotc else mp["kcols"],
+                   mp["afrag_c"] if rotc else mp["afrag"], int(rotc), Vp, I64(Vp.stride(0)), w0, w1, w2, I64(ncols),
+                   int(ncols), int(degree), float(lo_spec), float(lo_cut), float(hi))
+            return
         if self.d_code == -2 and aligned:
             dc, ix, vl = self.d_code, self.indices_k, self.vals_k
         else:
             dc, ix, vl = self.d, self.indices, self.vals
         if self._mma_ok(ncols, Vp, w0, w1):
             mp = self.mma
-            h.call("rvgp_cheb_filter_mma_f64", self.nbrows, self.d, mp["kptr"], mp["kcols"], mp["afrag"],
-                   Vp, I64(Vp.stride(0)), w0, w1, I64(w0.stride(0)), int(ncols), int(degree), float(lo_spec),
+            h.call("rvgp_cheb_filter_mma_f64", self.nbrows, self.d, mp["kptr"], mp["kcols"], mp["afrag"], 0,
+                   Vp, I64(Vp.stride(0)), w0, w1, None, I64(w0.stride(0)), int(ncols), int(degree), float(lo_spec),
                    float(lo_cut), float(hi))
             return
         if self._merged_ok(ncols, Vp, w0, w1):
@@ -340,6 +400,9 @@ def smallest_eigenpairs(A, k, upper_bound, lower_bound=0.0, tol=1e-12, nex=None,
     B2 = torch.empty((N, m), dtype=torch.float64, device=dev)
     w0 = torch.empty((N, panel), dtype=torch.float64, device=dev)
     w1 = torch.empty((N, panel), dtype=torch.float64, device=dev)
+    # third work panel: the MMA filter (d == 2) rotates three node-contiguous panels (BsrMatrix.cheb_filter)
+    w2 = torch.empty((N, panel), dtype=torch.float64, device=dev) if (getattr(A, "mma", None) is not None and A.d == 2) else None
+    st["spmm_kernel"] = "mma_native" if w2 is not None else "gather"
     Gd = torch.empty((m, m), dtype=torch.float64, device=dev)
     Hd = torch.empty((m, m), dtype=torch.float64, device=dev)
     Cd = torch.empty((m, m), dtype=torch.float64, device=dev)
@@ -366,7 +429,10 @@ def smallest_eigenpairs(A, k, upper_bound, lower_bound=0.0, tol=1e-12, nex=None,
             dg = int(deg[p0:p1].max())
             if dg <= 0:
                 continue
-            A.cheb_filter(V[:, p0:p1], w0, w1, p1 - p0, dg, lo_spec, float(a_cut), hi, h=h)
+            if w2 is not None and p1 - p0 == panel:
+                A.cheb_filter(V[:, p0:p1], w0, w1, p1 - p0, dg, lo_spec, float(a_cut), hi, h=h, w2=w2)
+            else:
+                A.cheb_filter(V[:, p0:p1], w0, w1, p1 - p0, dg, lo_spec, float(a_cut), hi, h=h)
             st["spmm_launches"] += dg
             st["filter_launches"] += dg
             st["filter_col_degrees"] += dg * (p1 - p0)

@@ -252,17 +252,18 @@ def test_spmm_merged_matches_scipy(case, ncols, R):
 
 @pytest.mark.parametrize("case", ["sphere_n2000_k50", "flat3torus_R6_n900_k24", "torus_n600_k20"])
 @pytest.mark.parametrize("ncols", [16, 32, 48, 64, 128])
-def test_spmm_mma_matches_scipy(case, ncols):
-    """K9 v4 (FP64 mma.sync row-group SpMM) == SciPy for the d = 2 connection Laplacian and the pattern-mode L,
-    on contiguous blocks and on column panels of a wider block vector; shapes the MMA path cannot take fall back."""
+def test_spmm_mma_rowmajor_matches_scipy(case, ncols):
+    """K9 v4a (row-major FP64 mma.sync row-group SpMM, kept as an experiment) == SciPy for the d = 2 connection
+    Laplacian and the pattern-mode L, on contiguous blocks and on column panels of a wider block vector; shapes the
+    MMA path cannot take fall back."""
     g = load_golden(case)
     for which in ("Lc", "L"):
         A, S = _bsr_from_golden(g, which)
         if A.d not in (1, 2):
-            assert A.enable_mma() is None
+            assert A.enable_mma(rowmajor=True) is None
             continue
-        mp = A.enable_mma()
-        assert mp["ksteps"] > 0 and 0.0 < mp["fill"] <= 1.0
+        mp = A.enable_mma(rowmajor=True)
+        assert mp["ksteps"] > 0 and 0.0 < mp["fill"] <= 1.0 and mp["afrag"] is not None
         rng = np.random.default_rng(5)
         X = rng.normal(size=(A.nrows, ncols)); W = rng.normal(size=(A.nrows, ncols))
         big = torch.zeros((A.nrows, ncols + 32), dtype=torch.float64, device=_dev())
@@ -285,18 +286,79 @@ def test_spmm_mma_matches_scipy(case, ncols):
         assert np.abs(Yo.cpu().numpy() - S @ big[:, 3:13].cpu().numpy()).max() <= 1e-12
 
 
-@pytest.mark.parametrize("degree", [1, 2, 9])
+def _native_cases():
+    return ["sphere_n2000_k50", "torus_n600_k20"]
+
+
+@pytest.mark.parametrize("case", _native_cases())
+@pytest.mark.parametrize("ncols", [16, 32, 64, 96, 128])
+@pytest.mark.parametrize("compact", [True, False])
+def test_spmm_mma_native_matches_scipy(case, ncols, compact):
+    """K9 v4 (shipped): FP64-MMA SpMM on node-contiguous panels == SciPy for the d = 2 connection Laplacian, with the full
+    and the compact (rotation + sign bit) fragment plans, all schedule variants, with / without W, and for a row count that
+    is not a multiple of the group size."""
+    from rvgp_b200.eigensolver import BsrMatrix
+    from rvgp_b200._cabi import get_handle
+    g = load_golden(case)
+    A, S = _bsr_from_golden(g, "Lc")
+    assert A.d == 2
+    h = get_handle(0)
+    for drop in (0, 3):       # drop trailing nodes: nbrows % 4 != 0
+        if drop:
+            n2 = A.nbrows - drop
+            ip = A.indptr[: n2 + 1].clone()
+            keep = (A.indices[: int(ip[-1])] < n2)
+            # rebuild a consistent CSR on the first n2 nodes
+            rows = torch.repeat_interleave(torch.arange(n2, device=_dev()), (ip[1:] - ip[:-1]).long())[keep]
+            ix = A.indices[: int(ip[-1])][keep].contiguous()
+            vl = A.vals[: int(ip[-1])][keep].contiguous()
+            ip2 = torch.zeros(n2 + 1, dtype=torch.int32, device=_dev())
+            ip2[1:] = torch.cumsum(torch.bincount(rows, minlength=n2), 0).to(torch.int32)
+            B = BsrMatrix(n2, 2, ip2, ix, vl)
+            Sm = sp.bsr_matrix((vl.cpu().numpy(), ix.cpu().numpy(), ip2.cpu().numpy()), shape=(2 * n2, 2 * n2)).tocsr()
+        else:
+            B, Sm = A, S
+        B._mma_plan = None
+        B.mma = B.build_mma_plan(compact=compact)
+        assert B.mma["rotc"] == (1 if compact else 0)
+        rng = np.random.default_rng(7)
+        X = rng.normal(size=(B.nrows, ncols)); W = rng.normal(size=(B.nrows, ncols))
+        Xd, Wd = torch.from_numpy(X).to(_dev()), torch.from_numpy(W).to(_dev())
+        Xn, Wn = B.to_native(Xd), B.to_native(Wd)
+        assert np.array_equal(B.from_native(Xn).cpu().numpy(), X)
+        ref = Sm @ X
+        try:
+            for var in (0, 1, 2, 3, 5, 6):
+                for gpw in (0, 2):
+                    h.set_option("mma_variant", var); h.set_option("mma_gpw", gpw)
+                    Yn = torch.full_like(Xn, 7.0)
+                    B.spmm_native(Xn, Yn)
+                    assert np.abs(B.from_native(Yn).cpu().numpy() - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max())
+                    B.spmm_native(Xn, Yn, alpha=0.7, beta=-1.3, gamma=0.25, Wn=Wn, reverse=(var & 1))
+                    ref2 = 0.7 * ref - 1.3 * X + 0.25 * W
+                    assert np.abs(B.from_native(Yn).cpu().numpy() - ref2).max() <= 1e-13 * max(1.0, np.abs(ref2).max())
+        finally:
+            h.set_option("mma_variant", 1); h.set_option("mma_gpw", 0)
+    with pytest.raises(ValueError):
+        A.spmm_native(Xn[:, :20], Yn[:, :20])          # 10 columns: not a multiple of 16
+
+
+@pytest.mark.parametrize("degree", [1, 2, 9, 40])
 def test_cheb_filter_mma_matches_gather(degree):
+    """The native-layout MMA filter (Lc, d = 2) and the row-major MMA filter (L) agree with the gather-kernel filter."""
     g = load_golden("sphere_n2000_k50")
     for which in ("Lc", "L"):
         A, _ = _bsr_from_golden(g, which)
         V0 = torch.from_numpy(np.random.default_rng(2).normal(size=(A.nrows, 96))).to(_dev())
         outs = []
         for on in (False, True):
-            A.enable_mma(on)
+            A.enable_mma(on, rowmajor=(which == "L"))
             V = V0.clone()
-            w0 = torch.empty((A.nrows, 32), dtype=torch.float64, device=_dev()); w1 = torch.empty_like(w0)
-            A.cheb_filter(V[:, 32:64], w0, w1, 32, degree, 0.0, 3.0, 40.0)
+            w0 = torch.empty((A.nrows, 32), dtype=torch.float64, device=_dev()); w1 = torch.empty_like(w0); w2 = torch.empty_like(w0)
+            if on and which == "Lc":
+                assert A._mma_native_ok(32, V[:, 32:64], w0, w1, w2)
+            A.cheb_filter(V[:, 32:64], w0, w1, 32, degree, 0.0, 3.0, 40.0, w2=w2)
             outs.append(V.cpu().numpy())
         assert np.abs(outs[0][:, :32] - V0[:, :32].cpu().numpy()).max() == 0.0
-        assert np.abs(outs[0] - outs[1]).max() <= 1e-12 * np.abs(outs[0]).max()
+        assert np.abs(outs[0][:, 64:] - V0[:, 64:].cpu().numpy()).max() == 0.0
+        assert np.abs(outs[0] - outs[1]).max() <= 1e-11 * np.abs(outs[0]).max()

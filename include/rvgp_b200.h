@@ -143,6 +143,44 @@ int rvgp_cheb_filter_mma_f64(rvgp_handle_t h, int nbrows, int d, const int32_t* 
                              const double* afrag, int rotc, double* V, int64_t ldv, double* work0, double* work1,
                              double* work2, int64_t ldw, int ncols, int degree, double lo_spec, double lo_cut, double hi);
 
+/* ---- Row-sharded operator with the halo exchange over NVLink peer memory (csrc/halo.cu) ------------
+ * The extended block vectors E[0..2] ((n_loc + n_halo) * d rows x ncols, contiguous; node-contiguous panels when an MMA
+ * plan is given) and the flag array live in memory allocated with rvgp_ipc_alloc and opened by the peers with
+ * rvgp_ipc_open (CUDA IPC; the 64-byte handles travel through torch.distributed).  pull_src[s][i] = peer-mapped address
+ * of the row of halo node i in its owner's E[s]; peer_slots[j] = peer-mapped address of THIS rank's slot in neighbour j's
+ * flag array; wait_idx[j] = slot of neighbour j in this rank's flag array.  Every call only enqueues kernels on the
+ * handle's stream (signal / wait / pull / SpMM per degree); epochs must grow monotonically and identically on all ranks:
+ * a filter consumes epoch0 .. epoch0 + degree, a product epoch0 .. epoch0 + 1.  err (device int32) is set when a wait
+ * times out (timeout_ms) -- the results are then undefined but nothing hangs. */
+typedef struct rvgp_halo_ctx {
+    int32_t n_loc, n_halo, d, ncols;
+    const int32_t* indptr;          /* local block rows, columns renumbered to [local | halo] */
+    const int32_t* indices;
+    const double* vals;             /* NULL: unit-weight graph Laplacian pattern (d == 1) */
+    const int32_t* kptr;            /* optional MMA plan of the local matrix (d == 2), else NULL */
+    const int32_t* kcols;
+    const double* afrag;
+    int32_t rotc;
+    int32_t n_peers;
+    double* E[3];
+    const int64_t* pull_src[3];
+    uint64_t* flags;
+    uint64_t** peer_slots;
+    const int32_t* wait_idx;
+    int32_t* err;
+    int32_t timeout_ms;
+    int32_t reserved;
+} rvgp_halo_ctx;
+int rvgp_ipc_alloc(rvgp_handle_t h, int64_t bytes, void** dptr, uint8_t* handle64);
+int rvgp_ipc_open(rvgp_handle_t h, const uint8_t* handle64, void** dptr);
+int rvgp_ipc_close(rvgp_handle_t h, void* dptr);
+int rvgp_ipc_free(rvgp_handle_t h, void* dptr);
+int rvgp_halo_barrier(rvgp_handle_t h, const rvgp_halo_ctx* ctx, uint64_t epoch);
+int rvgp_halo_spmm_f64(rvgp_handle_t h, const rvgp_halo_ctx* ctx, uint64_t epoch0, const double* X, int64_t ldx, double* Y,
+                       int64_t ldy);
+int rvgp_halo_cheb_filter_f64(rvgp_handle_t h, const rvgp_halo_ctx* ctx, uint64_t epoch0, double* V, int64_t ldv, int degree,
+                              double lo_spec, double lo_cut, double hi);
+
 /* ---- K10: dense FP64 kernels for orthogonalisation / Rayleigh-Ritz ---------------------------------
  * C (m x n, ldc) = alpha * op(A) * op(B).  Layout flags say which index of each operand is contiguous:
  *   a_kmajor = 0: A(i,k) = A[k*lda + i]  ("A is stored as K x M", e.g. V^T of a tall block vector)

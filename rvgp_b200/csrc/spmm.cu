@@ -385,6 +385,12 @@ static int spmm_dispatch(Handle* h, int nbrows, int d, const int* indptr, const 
     }
 }
 
+int spmm_dispatch_public(Handle* h, int nbrows, int d, const int* indptr, const int* indices, const double* vals,
+                         const double* X, int64_t ldx, const double* W, int64_t ldw, double* Y, int64_t ldy, int ncols,
+                         double alpha, double beta, double gamma) {
+    return spmm_dispatch(h, nbrows, d, indptr, indices, vals, X, ldx, W, ldw, Y, ldy, ncols, alpha, beta, gamma);
+}
+
 }  // namespace rvgp
 
 using namespace rvgp;

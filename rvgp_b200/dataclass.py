@@ -163,7 +163,9 @@ class data:
             plan = HaloPlan(p_indptr, p_indices, bounds, rank)
             plan.exchange_requests()
             S_L = ShardedBsr(plan, 1, None, comm)
-            S_Lc = ShardedBsr(plan, dim_man, Lc_vals_p[plan.e0:plan.e1].contiguous(), comm)
+            S_Lc = ShardedBsr(plan, dim_man, plan.local_values(Lc_vals_p), comm)
+            if dim_man == 2 and os.environ.get("RVGP_SPMM_MMA", "1") != "0" and os.environ.get("RVGP_PEER_HALO", "1") != "0":
+                self.stats["spmm_mma"] = S_Lc.enable_mma() is not None
             counts = [int(bounds[r + 1] - bounds[r]) for r in range(world)]
             self.stats["halo"] = dict(n_loc=plan.n_loc, n_halo=plan.n_halo, send=sum(plan.send_counts))
             evals_L, U_loc = smallest_eigenpairs(S_L, k_L, upper_bound=hi, tol=eig_tol, stats=st_L, comm=comm)

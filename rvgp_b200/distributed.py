@@ -50,12 +50,21 @@ class HaloPlan:
         rowlen = (self.indptr_loc[1:] - self.indptr_loc[:-1]).to(torch.int64)
         rowid = torch.repeat_interleave(torch.arange(self.n_loc, device=dev), rowlen)
         self.boundary_rows = torch.unique(rowid[outside]).to(torch.int32).contiguous()
+        # keep every row's columns SORTED after the renumbering (halo nodes owned by lower ranks moved behind the local
+        # ones): the row-group merge / MMA plans walk sorted column lists.  entry_perm reorders per-entry values alike.
+        key = rowid * (self.n_loc + self.n_halo + 1) + self.indices_loc.to(torch.int64)
+        self.entry_perm = torch.argsort(key)
+        self.indices_loc = self.indices_loc[self.entry_perm].contiguous()
         # how many halo nodes come from each peer
         b = torch.tensor(self.bounds, dtype=torch.int64, device=dev)
         owner = torch.searchsorted(b, halo, right=True) - 1 if self.n_halo else halo
         self.recv_counts = [int((owner == q).sum().item()) for q in range(self.world)]
         self.send_counts = [0] * self.world
         self.send_ids = torch.zeros(0, dtype=torch.int32, device=dev)
+
+    def local_values(self, vals_global):
+        """This rank's per-entry values, in the (column-sorted) entry order of indices_loc."""
+        return vals_global[self.e0:self.e1][self.entry_perm.to(vals_global.device)].contiguous()
 
     def exchange_requests(self):
         """Tell every owner which of its nodes this rank needs (one-time setup).  After this, ``send_ids`` lists the
@@ -143,10 +152,143 @@ class Comm:
         return torch.cat([o[: int(c)] for o, c in zip(outs, counts)], 0)
 
 
+class _DevMem:
+    """A raw device allocation exposed to torch through __cuda_array_interface__ (no copy, no ownership)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 3}
+
+
+class PeerHalo:
+    """Halo exchange over NVLink peer memory for one (ShardedBsr, ncols): the three extended block vectors and a flag array
+    are allocated with rvgp_ipc_alloc, the 64-byte CUDA IPC handles are exchanged once through torch.distributed, and from
+    then on a whole Chebyshev recurrence is ONE C call (rvgp_halo_cheb_filter_f64: signal / wait / pull / SpMM kernels per
+    degree, no NCCL, no host round trip).  See csrc/halo.cu for the protocol."""
+
+    def __init__(self, op, ncols, timeout_ms=20000):
+        import ctypes
+        from ._cabi import get_handle
+        plan, d = op.plan, op.d
+        self.op, self.ncols = op, int(ncols)
+        dev = op.indptr.device
+        self.h = h = get_handle(dev.index)
+        lib = h.lib
+        world, rank, group = plan.world, plan.rank, plan.group
+        row_bytes = d * self.ncols * 8
+        ebytes = max(256, (plan.n_loc + plan.n_halo) * row_bytes)
+        self._own, self._opened = [], []
+
+        def shared(nbytes):
+            ptr = ctypes.c_void_p()
+            hd = (ctypes.c_uint8 * 64)()
+            rc = lib.rvgp_ipc_alloc(h._h, ctypes.c_int64(nbytes), ctypes.byref(ptr), hd)
+            if rc != 0:
+                raise RuntimeError("rvgp_ipc_alloc: " + lib.rvgp_last_error(h._h).decode())
+            self._own.append(ptr.value)
+            gathered = [None] * world
+            dist.all_gather_object(gathered, bytes(hd), group=group)
+            ptrs = []
+            for q in range(world):
+                if q == rank:
+                    ptrs.append(ptr.value)
+                    continue
+                pp = ctypes.c_void_p()
+                hq = (ctypes.c_uint8 * 64).from_buffer_copy(gathered[q])
+                rc = lib.rvgp_ipc_open(h._h, hq, ctypes.byref(pp))
+                if rc != 0:
+                    raise RuntimeError("rvgp_ipc_open: " + lib.rvgp_last_error(h._h).decode())
+                self._opened.append(pp.value)
+                ptrs.append(pp.value)
+            return ptrs
+
+        self.E_ptrs = [shared(ebytes) for _ in range(3)]              # [slot][rank] -> device address
+        self.flag_ptrs = shared(8 * max(world, 32))
+        nrows_ext = (plan.n_loc + plan.n_halo) * d
+        self.E = [torch.as_tensor(_DevMem(self.E_ptrs[s][rank], ebytes), device=dev).view(torch.float64)[: nrows_ext * self.ncols]
+                  .view(nrows_ext, self.ncols) for s in range(3)]
+        # pull tables: address of every halo node's row in its owner's buffer
+        b = torch.tensor(plan.bounds, dtype=torch.int64, device=dev)
+        halo = plan.halo_ids
+        owner = (torch.searchsorted(b, halo, right=True) - 1) if plan.n_halo else halo
+        self.pull = []
+        for s in range(3):
+            base = torch.tensor(self.E_ptrs[s], dtype=torch.int64, device=dev)
+            src = (base[owner] + (halo - b[owner]) * row_bytes) if plan.n_halo else torch.zeros(1, dtype=torch.int64, device=dev)
+            self.pull.append(src.contiguous())
+        peers = [q for q in range(world) if q != rank and (plan.recv_counts[q] > 0 or plan.send_counts[q] > 0)]
+        self.peers = peers
+        self.peer_slots = torch.tensor([self.flag_ptrs[q] + 8 * rank for q in peers] or [0], dtype=torch.int64, device=dev)
+        self.wait_idx = torch.tensor(peers or [0], dtype=torch.int32, device=dev)
+        self.err = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.epoch = 1
+        L = op.local
+        mp = L.mma if (d == 2 and getattr(L, "mma", None) is not None and self.ncols % 16 == 0) else None
+        self.kernel = "mma_native" if mp is not None else "gather"
+
+        class Ctx(ctypes.Structure):
+            _fields_ = [("n_loc", ctypes.c_int32), ("n_halo", ctypes.c_int32), ("d", ctypes.c_int32), ("ncols", ctypes.c_int32),
+                        ("indptr", ctypes.c_void_p), ("indices", ctypes.c_void_p), ("vals", ctypes.c_void_p),
+                        ("kptr", ctypes.c_void_p), ("kcols", ctypes.c_void_p), ("afrag", ctypes.c_void_p),
+                        ("rotc", ctypes.c_int32), ("n_peers", ctypes.c_int32),
+                        ("E", ctypes.c_void_p * 3), ("pull_src", ctypes.c_void_p * 3),
+                        ("flags", ctypes.c_void_p), ("peer_slots", ctypes.c_void_p), ("wait_idx", ctypes.c_void_p),
+                        ("err", ctypes.c_void_p), ("timeout_ms", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+        c = Ctx()
+        c.n_loc, c.n_halo, c.d, c.ncols = plan.n_loc, plan.n_halo, d, self.ncols
+        c.indptr, c.indices = L.indptr.data_ptr(), L.indices.data_ptr()
+        c.vals = L.vals.data_ptr() if L.vals is not None else None
+        if mp is not None:
+            rotc = mp["rotc"]
+            c.kptr = mp["kptr"].data_ptr()
+            c.kcols = (mp["kcols_c"] if rotc else mp["kcols"]).data_ptr()
+            c.afrag = (mp["afrag_c"] if rotc else mp["afrag"]).data_ptr()
+            c.rotc = int(rotc)
+        c.n_peers = len(peers)
+        for s in range(3):
+            c.E[s] = self.E_ptrs[s][rank]
+            c.pull_src[s] = self.pull[s].data_ptr()
+        c.flags = self.flag_ptrs[rank]
+        c.peer_slots, c.wait_idx, c.err = self.peer_slots.data_ptr(), self.wait_idx.data_ptr(), self.err.data_ptr()
+        c.timeout_ms = int(timeout_ms)
+        self.ctx = c
+        self._cp = ctypes.pointer(c)
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=group)                    # every rank has opened every handle before the first pull
+
+    def cheb_filter(self, Vp, degree, lo_spec, lo_cut, hi):
+        from ._cabi import I64, U64
+        self.h.sync_stream()
+        self.h.call("rvgp_halo_cheb_filter_f64", self._cp, U64(self.epoch), Vp, I64(Vp.stride(0)), int(degree), float(lo_spec),
+                    float(lo_cut), float(hi))
+        self.epoch += int(degree) + 1
+
+    def spmm(self, X, Y):
+        from ._cabi import I64, U64
+        self.h.sync_stream()
+        self.h.call("rvgp_halo_spmm_f64", self._cp, U64(self.epoch), X, I64(X.stride(0)), Y, I64(Y.stride(0)))
+        self.epoch += 2
+
+    def check(self):
+        if int(self.err.item()) != 0:
+            raise RuntimeError("peer halo exchange timed out waiting for a neighbour rank (rvgp_halo_ctx.err)")
+
+    def close(self):
+        lib, hh = self.h.lib, self.h._h
+        import ctypes
+        for p in self._opened:
+            lib.rvgp_ipc_close(hh, ctypes.c_void_p(p))
+        for p in self._own:
+            lib.rvgp_ipc_free(hh, ctypes.c_void_p(p))
+        self._opened, self._own = [], []
+
+
 class ShardedBsr:
     """This rank's rows of a BSR matrix plus the halo machinery; duck-types eigensolver.BsrMatrix."""
 
     def __init__(self, plan, d, vals_loc, comm):
+        """vals_loc: the blocks of this rank's entries in the plan's entry order, i.e. global_vals[plan.e0:plan.e1][plan.entry_perm]
+        (``plan.local_values`` does that)."""
         from .eigensolver import BsrMatrix
         self.plan, self.d, self.comm = plan, int(d), comm
         self.local = BsrMatrix(plan.n_loc, d, plan.indptr_loc, plan.indices_loc, vals_loc)
@@ -157,6 +299,40 @@ class ShardedBsr:
         self.nnzb = self.local.nnzb
         self._bufs = {}
         self.row_offset = plan.r0 * self.d
+        self._peer = {}                 # ncols -> PeerHalo (or None when CUDA IPC is unavailable)
+        self.mma = None
+
+    peer_halo = True                    # halo exchange by our own kernels over NVLink peer memory (csrc/halo.cu)
+
+    @property
+    def spmm_kernel_name(self):
+        ph = [p for p in self._peer.values() if p is not None]
+        if ph:
+            return ph[0].kernel + " + peer-memory halo"
+        return "gather + nccl halo"
+
+    def enable_mma(self, on=True, h=None):
+        """FP64-MMA SpMM for the local rows (d == 2); only used by the peer-memory path."""
+        self.mma = self.local.enable_mma(on, h=h) if self.d == 2 else None
+        return self.mma
+
+    def _peer_for(self, ncols):
+        """PeerHalo for this panel width, built collectively on first use (all ranks take the same path)."""
+        import os
+        if not (self.peer_halo and self.indptr.is_cuda and self.plan.world > 1 and ncols % 2 == 0
+                and os.environ.get("RVGP_PEER_HALO", "1") != "0"):
+            return None
+        if ncols not in self._peer:
+            ok = torch.ones(1, dtype=torch.int32, device=self.indptr.device)
+            ph = None
+            try:
+                ph = PeerHalo(self, ncols)
+            except Exception as e:                      # no CUDA IPC between these devices: keep the NCCL exchange
+                print("rvgp_b200: peer-memory halo exchange unavailable (%s); using NCCL all_to_all" % (e,))
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.plan.group)
+            self._peer[ncols] = ph if int(ok.item()) == 1 else None
+        return self._peer[ncols]
 
     def spmm_bytes(self, ncols, fused=False):
         return self.local.spmm_bytes(ncols, fused)
@@ -210,6 +386,12 @@ class ShardedBsr:
             out = torch.empty_like(X)
         for c0 in range(0, X.shape[1], 64):
             c1 = min(X.shape[1], c0 + 64)
+            ph = self._peer_for(c1 - c0) if (c1 - c0) == 64 else None
+            if ph is not None:
+                ph.spmm(X[:, c0:c1], out[:, c0:c1])
+                if c1 == X.shape[1]:
+                    ph.check()
+                continue
             E = self._ext(c1 - c0, 0)
             E[: self.nrows].copy_(X[:, c0:c1])
             tmp = self._ext(c1 - c0, 1)
@@ -217,9 +399,13 @@ class ShardedBsr:
             out[:, c0:c1].copy_(tmp[: self.nrows])
         return out
 
-    def cheb_filter(self, Vp, w0, w1, ncols, degree, lo_spec, lo_cut, hi, h=None):
+    def cheb_filter(self, Vp, w0, w1, ncols, degree, lo_spec, lo_cut, hi, h=None, w2=None):
         """Same recurrence as rvgp_cheb_filter_f64, one halo exchange + one fused SpMM launch per degree."""
         if degree <= 0:
+            return
+        ph = self._peer_for(ncols) if ncols >= 16 else None
+        if ph is not None:
+            ph.cheb_filter(Vp, degree, lo_spec, lo_cut, hi)
             return
         E = [self._ext(ncols, s) for s in range(3)]
         E[0][: self.nrows].copy_(Vp)

@@ -401,7 +401,9 @@ def smallest_eigenpairs(A, k, upper_bound, lower_bound=0.0, tol=1e-12, nex=None,
     w0 = torch.empty((N, panel), dtype=torch.float64, device=dev)
     w1 = torch.empty((N, panel), dtype=torch.float64, device=dev)
     # third work panel: the MMA filter (d == 2) rotates three node-contiguous panels (BsrMatrix.cheb_filter)
-    w2 = torch.empty((N, panel), dtype=torch.float64, device=dev) if (getattr(A, "mma", None) is not None and A.d == 2) else None
+    w2 = None
+    if isinstance(A, BsrMatrix) and A.mma is not None and A.d == 2:
+        w2 = torch.empty((N, panel), dtype=torch.float64, device=dev)
     st["spmm_kernel"] = "mma_native" if w2 is not None else "gather"
     Gd = torch.empty((m, m), dtype=torch.float64, device=dev)
     Hd = torch.empty((m, m), dtype=torch.float64, device=dev)
@@ -496,6 +498,8 @@ def smallest_eigenpairs(A, k, upper_bound, lower_bound=0.0, tol=1e-12, nex=None,
         a_cut = max(a_cut, lo_spec + 1e-12 * (hi - lo_spec) + theta[k - 1] * (1 + 1e-9))
         deg = _next_degrees(theta, res, k, tol_abs, a_cut, hi, lo_spec, cond_max)
 
+    if not isinstance(A, BsrMatrix) and hasattr(A, "spmm_kernel_name"):
+        st["spmm_kernel"] = A.spmm_kernel_name
     st["residual_max"] = float(res[:k].max())
     st["converged"] = bool((res[:k] <= tol_abs).all())
     evals = theta_d[:k].clone()

@@ -38,8 +38,11 @@ def _worker(rank, world, port, case, d, q):
         plan = HaloPlan(torch.from_numpy(indptr), torch.from_numpy(indices), bounds, rank)
         plan.exchange_requests()
         assert sum(plan.recv_counts) == plan.n_halo and plan.recv_counts[rank] == 0
+        # every local row keeps sorted columns after the [local | halo] renumbering (the MMA / merge plans rely on it)
+        ipl, ixl = plan.indptr_loc.numpy(), plan.indices_loc.numpy()
+        assert all(np.all(np.diff(ixl[ipl[i]:ipl[i + 1]]) > 0) for i in range(plan.n_loc))
         # local matrix in [local | halo] numbering
-        Aloc = sp.bsr_matrix((blocks[plan.e0:plan.e1], plan.indices_loc.numpy(), plan.indptr_loc.numpy()),
+        Aloc = sp.bsr_matrix((plan.local_values(torch.from_numpy(blocks)).numpy(), plan.indices_loc.numpy(), plan.indptr_loc.numpy()),
                              shape=(plan.n_loc * d, (plan.n_loc + plan.n_halo) * d))
         rng = np.random.default_rng(0)
         X = rng.normal(size=(n * d, 5))                               # same global vector on every rank

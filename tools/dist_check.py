@@ -26,13 +26,15 @@ def main():
     # timing at C2 scale
     from tests.workloads import make_cloud
     X = make_cloud("torus", int(os.environ.get("DIST_N", "200000")), 0)
-    for shard in (True, False):
+    for shard, peer in ((True, "1"), (True, "0"), (False, "1")):
+        os.environ["RVGP_PEER_HALO"] = peer
         torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
         d = data(X, n_eigenpairs=200, verbose=False, shard=shard)
         torch.cuda.synchronize(); dist.barrier()
         if rank == 0:
-            print("n=%d k=200 shard=%s world=%d: %.2f s  stages %s  eig_Lc %s halo %s" % (len(X), shard, world, time.perf_counter() - t0,
-                  {a: round(b, 2) for a, b in d.timings.items()}, {a: d.stats["eig_Lc"][a] for a in ("outer", "filter_launches", "t_filter", "t_dense")}, d.stats.get("halo")))
+            print("n=%d k=200 shard=%s peer_halo=%s world=%d: %.2f s  stages %s  eig_Lc %s halo %s" % (len(X), shard, peer, world, time.perf_counter() - t0,
+                  {a: round(b, 2) for a, b in d.timings.items()}, {a: d.stats["eig_Lc"][a] for a in ("outer", "filter_launches", "t_filter", "t_dense", "spmm_kernel")}, d.stats.get("halo")))
+    os.environ["RVGP_PEER_HALO"] = "1"
     if rank == 0:
         print("DIST_CHECK", "PASS" if ok else "FAIL")
     dist.destroy_process_group()

@@ -279,7 +279,8 @@ int rvgp_frame_apply(rvgp_handle_t h, const double* gauges, int64_t n, int D, in
 
 /* ---- K1: furthest-point sampling (geometry.py:126-162), one persistent cooperative kernel ---------------
  * N > 0: exactly N samples; N == 0: until lambdas[i]/diam < spacing (diam = max pairwise distance, computed
- * here with sklearn's euclidean_distances expansion).  perm/lambdas capacity: N, or n when N == 0. */
+ * here with sklearn's euclidean_distances expansion).  perm/lambdas capacity: N, or n when N == 0.  D <= 1024; for D > 64
+ * (feature-space sampling of SGPR inducing points, main.py:60) one warp owns a point and lanes stride over coordinates. */
 int rvgp_fps_f64(rvgp_handle_t h, const double* X, int n, int D, int N, double spacing, int start_idx,
                  int32_t* perm, double* lambdas, int32_t* count_out, void* workspace, int64_t workspace_bytes);
 int64_t rvgp_fps_workspace_bytes(rvgp_handle_t h, int n);
@@ -320,6 +321,25 @@ int rvgp_kdiag_f64(rvgp_handle_t h, const double* X, int64_t ldx, int64_t n, int
 int rvgp_gp_lowrank_small_f64(rvgp_handle_t h, int nprob, int k, const double* G, int64_t g_stride, const double* b,
                               int64_t b_stride, const double* yy, const double* Mrows, const double* s, int64_t s_stride,
                               const double* noise, double* out, int64_t out_stride, int want_predict);
+
+/* ---- K17: squared-exponential kernel for train_gp(kernel='rbf') (main.py:33-37 -> gpflow.kernels.RBF())
+ * and the dense pieces of the SGPR path (main.py:59-67,119-137 -> gpflow.models.SGPR).
+ * rvgp_rbf_from_dot_f64: K[i,j] = variance * exp(-0.5 * (xa2[i] + xb2[j] - 2 P[i,j]) / lengthscale^2), P = XA XB^T from
+ *   rvgp_dgemm_f64, xa2/xb2 = squared row norms (rvgp_kdiag_f64 with S = 1).  Kout may alias P.
+ * rvgp_rbf_adjoint_f64: reverse mode of the same map for an adjoint Gbar (m x n): H = Gbar o K (Hout nullable, may alias
+ *   Gbar or P), sums[0] = sum H, sums[1] = sum H * r2 (r2 scaled by 1/l^2), rowsum[i] = sum_j H[i,j] (nullable).
+ *   dF/dvariance = sums[0] / variance, dF/dlengthscale = sums[1] / lengthscale.  Deterministic two-stage reduction.
+ * rvgp_rbf_dx_f64: out = (HX - rowsum o XA) / l^2 = dF/dXA (gradient w.r.t. inducing points).
+ * rvgp_scale_shift_f64: A = alpha * A + beta * I (rectangular allowed). */
+int rvgp_rbf_from_dot_f64(rvgp_handle_t h, int m, int n, const double* P, int64_t ldp, const double* xa2,
+                          const double* xb2, double variance, double lengthscale, double* Kout, int64_t ldk);
+int rvgp_rbf_adjoint_f64(rvgp_handle_t h, int m, int n, const double* Gbar, int64_t ldg, const double* P, int64_t ldp,
+                         const double* xa2, const double* xb2, double variance, double lengthscale, double* Hout,
+                         int64_t ldh, double* rowsum, double* sums, void* workspace, int64_t workspace_bytes);
+int64_t rvgp_rbf_adjoint_workspace_bytes(int m, int n);
+int rvgp_rbf_dx_f64(rvgp_handle_t h, int64_t m, int k, const double* HX, int64_t ldhx, const double* rowsum,
+                    const double* XA, int64_t ldx, double lengthscale, double* out, int64_t ldo);
+int rvgp_scale_shift_f64(rvgp_handle_t h, int64_t nrows, int ncols, double alpha, double beta, double* A, int64_t lda);
 
 #ifdef __cplusplus
 }

@@ -39,7 +39,8 @@ __device__ __forceinline__ Best better(Best a, Best b) {   // larger value wins;
     return (b.v > a.v || (b.v == a.v && b.i < a.i)) ? b : a;
 }
 
-constexpr int FPS_MAXD = 64;
+constexpr int FPS_MAXD = 1024;       // feature-space FPS for SGPR inducing points: D = n_eigenpairs (main.py:60)
+constexpr int FPS_THREAD_MAXD = 64;  // above this one WARP (not one thread) owns a point: coalesced row reads
 
 __global__ void __launch_bounds__(256)
 fps_kernel(const double* __restrict__ X, const double* __restrict__ xx, int n, int D, int n_out, int use_spacing,
@@ -58,15 +59,31 @@ fps_kernel(const double* __restrict__ X, const double* __restrict__ xx, int n, i
     int produced = 1;
     for (int step = 1; step < n_out; ++step) {
         // row `cur` of the distance matrix -> ds = min(ds, D[cur]) (step 1: ds = D[start])
-        if (threadIdx.x < D) xi[threadIdx.x] = X[(int64_t)cur * D + threadIdx.x];
+        for (int k = threadIdx.x; k < D; k += blockDim.x) xi[k] = X[(int64_t)cur * D + k];
         __syncthreads();
         const double xxi = xx[cur];
         Best b{-1.0, 0x7fffffff};
-        for (int j = tid; j < n; j += nth) {
-            double d = (j == cur) ? 0.0 : sqrt(sk_dist2(X, xx, D, xi, xxi, j));
-            if (step > 1) d = fmin(ds[j], d);
-            ds[j] = d;
-            if (d > b.v) { b.v = d; b.i = j; }        // ascending j: strict > keeps the first maximum
+        if (D <= FPS_THREAD_MAXD) {
+            for (int j = tid; j < n; j += nth) {
+                double d = (j == cur) ? 0.0 : sqrt(sk_dist2(X, xx, D, xi, xxi, j));
+                if (step > 1) d = fmin(ds[j], d);
+                ds[j] = d;
+                if (d > b.v) { b.v = d; b.i = j; }        // ascending j: strict > keeps the first maximum
+            }
+        } else {
+            // high-dimensional rows (feature space): lanes stride over the coordinates, every lane ends with the same d
+            for (int j = tid >> 5; j < n; j += nth >> 5) {
+                double dot = 0.0;
+                for (int k = lane; k < D; k += 32) dot = fma(xi[k], __ldg(X + (int64_t)j * D + k), dot);
+                dot = warp_sum(dot);
+                double d = -2.0 * dot;
+                d = __dadd_rn(d, xxi);
+                d = __dadd_rn(d, __ldg(xx + j));
+                d = (j == cur) ? 0.0 : sqrt(d > 0.0 ? d : 0.0);
+                if (step > 1) d = fmin(ds[j], d);
+                if (lane == 0) ds[j] = d;
+                if (d > b.v) { b.v = d; b.i = j; }
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -165,7 +182,7 @@ extern "C" int64_t rvgp_fps_workspace_bytes(rvgp_handle_t hh, int n) {
 extern "C" int rvgp_fps_f64(rvgp_handle_t hh, const double* X, int n, int D, int N, double spacing, int start_idx,
                             int32_t* perm, double* lambdas, int32_t* count_out, void* workspace, int64_t workspace_bytes) {
     Handle* h = H(hh);
-    RVGP_REQUIRE(h, n >= 1 && D >= 1 && D <= FPS_MAXD, "fps: D must be in [1,64]");
+    RVGP_REQUIRE(h, n >= 1 && D >= 1 && D <= FPS_MAXD, "fps: D must be in [1,1024]");
     RVGP_REQUIRE(h, start_idx >= 0 && start_idx < n && N >= 0 && N <= n, "fps: bad start_idx / N");
     if (rvgp_fps_workspace_bytes(hh, n) > workspace_bytes) return set_error(h, RVGP_ERR_CAPACITY, "fps: workspace too small%s%s");
     int blocks = h->sm_count;

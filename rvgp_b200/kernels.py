@@ -87,3 +87,141 @@ class ManifoldKernel:
 
     def __call__(self, X, X2=None, full_cov=True):
         return self.K(X, X2) if full_cov else self.K_diag(X)
+
+    # ---- generic kernel interface used by gp_general.DenseGPR / DeviceSGPR (device tensors in and out) ----------
+    def _gram(self, XA, XB, out=None):
+        h = get_handle(XA.device.index)
+        S = torch.from_numpy(self.eval_S(typ=self.typ)).to(XA.device)
+        if out is None:
+            out = torch.empty((XA.shape[0], XB.shape[0]), dtype=torch.float64, device=XA.device)
+        _dgemm(h, XA.shape[0], XB.shape[0], XA.shape[1], XA, XA.stride(0), 1, XB, XB.stride(0), 1, out, out.stride(0),
+               scale_k=S)
+        return out
+
+    def _diag(self, X):
+        return self.K_diag(X)
+
+    def _chain(self, dS):
+        """dF/dS (host k-vector) -> {parameter name: dF/d(constrained value)}."""
+        _, dSd = self.eval_S(typ=self.typ, grads=True)
+        names = (['nu'] if self.typ == 'matern' else []) + ['kappa', 'sigma_f']
+        return {n: float(dS @ dSd[n]) for n in names}
+
+    def _adjoint(self, XA, XB, Gbar, want_dX=False):
+        """Reverse mode of K(XA, XB) = (XA * S) XB^T for the adjoint Gbar (A x B): parameter gradients and dF/dXA.
+        T = Gbar XB (dgemm), dS_j = sum_a XA[a,j] T[a,j] (column reduction), dXA = T * S (column scaling)."""
+        h = get_handle(XA.device.index)
+        A, B, k = XA.shape[0], XB.shape[0], XA.shape[1]
+        T = torch.empty((A, k), dtype=torch.float64, device=XA.device)
+        split, sws = _splitk(B, A * k, XA.device)
+        _dgemm(h, A, k, B, Gbar, Gbar.stride(0), 1, XB, XB.stride(0), 0, T, T.stride(0), split_k=split, ws=sws)
+        dS = torch.empty(k, dtype=torch.float64, device=XA.device)
+        ws = torch.empty(max(1, h.query("rvgp_coldot_workspace_bytes", I64(A), int(k)) // 8), dtype=torch.float64,
+                         device=XA.device)
+        h.call("rvgp_coldot_f64", I64(A), int(k), XA, I64(XA.stride(0)), T, I64(T.stride(0)), dS, ws)
+        grads = self._chain(dS.cpu().numpy())
+        if not want_dX:
+            return grads, None
+        S = torch.from_numpy(self.eval_S(typ=self.typ)).to(XA.device)
+        h.call("rvgp_colscale_f64", I64(A), int(k), T, I64(T.stride(0)), S)
+        return grads, T
+
+    def _diag_adjoint_uniform(self, X, g, cache):
+        """Reverse mode of sum_f g * K_diag(X)[f] with one scalar weight g (the SGPR trace term):
+        dS_j = g * sum_f X[f,j]^2; the column sums are data-only and cached by the caller."""
+        if "colsq" not in cache:
+            h = get_handle(X.device.index)
+            k = X.shape[1]
+            out = torch.empty(k, dtype=torch.float64, device=X.device)
+            ws = torch.empty(max(1, h.query("rvgp_coldot_workspace_bytes", I64(X.shape[0]), int(k)) // 8),
+                             dtype=torch.float64, device=X.device)
+            h.call("rvgp_coldot_f64", I64(X.shape[0]), int(k), X, I64(X.stride(0)), X, I64(X.stride(0)), out, ws)
+            cache["colsq"] = out.cpu().numpy()
+        return self._chain(g * cache["colsq"])
+
+
+def _splitk(K, out_elems, dev):
+    """Deterministic split-K factor (and workspace) for products with a long contraction and a small output."""
+    split = max(1, min(64, K // 2048)) if K >= 4096 else 1
+    return split, (torch.empty(split * out_elems, dtype=torch.float64, device=dev) if split > 1 else None)
+
+
+def _sq_row_norms(h, X):
+    out = torch.empty(X.shape[0], dtype=torch.float64, device=X.device)
+    ones = torch.ones(X.shape[1], dtype=torch.float64, device=X.device)
+    h.call("rvgp_kdiag_f64", X, I64(X.stride(0)), I64(X.shape[0]), int(X.shape[1]), ones, out)
+    return out
+
+
+class RBF:
+    """Stand-in for ``gpflow.kernels.RBF()`` (= SquaredExponential), the channel-wise baseline of
+    ``train_gp(kernel='rbf')`` (RVGP/main.py:33-37):  K = variance * exp(-0.5 |x/l - x'/l|^2), K_diag = variance,
+    parameters ``variance`` and ``lengthscales`` (both 1.0, positive transform with the default positive minimum at
+    construction time).  Inner products on the FP64 dgemm, the elementwise part and its adjoint in csrc/gp_rbf.cu."""
+
+    typ = 'rbf'
+
+    def __init__(self, variance=1.0, lengthscales=1.0):
+        self.variance = P.Parameter(variance, transform=P.positive(), name='variance')
+        self.lengthscales = P.Parameter(lengthscales, transform=P.positive(), name='lengthscales')
+
+    @property
+    def trainable_parameters(self):
+        return [p for p in (self.variance, self.lengthscales) if p.trainable]
+
+    def _gram(self, XA, XB, out=None):
+        h = get_handle(XA.device.index)
+        if out is None:
+            out = torch.empty((XA.shape[0], XB.shape[0]), dtype=torch.float64, device=XA.device)
+        _dgemm(h, XA.shape[0], XB.shape[0], XA.shape[1], XA, XA.stride(0), 1, XB, XB.stride(0), 1, out, out.stride(0))
+        xa2 = _sq_row_norms(h, XA)
+        xb2 = xa2 if XB is XA else _sq_row_norms(h, XB)
+        h.call("rvgp_rbf_from_dot_f64", int(XA.shape[0]), int(XB.shape[0]), out, I64(out.stride(0)), xa2, xb2,
+               float(self.variance.value), float(self.lengthscales.value), out, I64(out.stride(0)))
+        return out
+
+    def _diag(self, X):
+        return torch.full((X.shape[0],), self.variance.value, dtype=torch.float64, device=X.device)
+
+    def K(self, X, X2=None):
+        Xd = to_device_f64(X).contiguous()
+        X2d = Xd if X2 is None else to_device_f64(X2, Xd.device).contiguous()
+        return self._gram(Xd, X2d)
+
+    def K_diag(self, X):
+        return self._diag(to_device_f64(X))
+
+    def __call__(self, X, X2=None, full_cov=True):
+        return self.K(X, X2) if full_cov else self.K_diag(X)
+
+    def _adjoint(self, XA, XB, Gbar, want_dX=False):
+        """Reverse mode of K(XA, XB) for the adjoint Gbar: {variance, lengthscales} gradients and dF/dXA.
+        Gbar is overwritten with H = Gbar o K when dF/dXA is wanted."""
+        h = get_handle(XA.device.index)
+        A, B, k = XA.shape[0], XB.shape[0], XA.shape[1]
+        dev = XA.device
+        Pm = torch.empty((A, B), dtype=torch.float64, device=dev)
+        _dgemm(h, A, B, k, XA, XA.stride(0), 1, XB, XB.stride(0), 1, Pm, Pm.stride(0))
+        xa2 = _sq_row_norms(h, XA)
+        xb2 = xa2 if XB is XA else _sq_row_norms(h, XB)
+        wsb = h.query("rvgp_rbf_adjoint_workspace_bytes", int(A), int(B))
+        ws = torch.empty(max(8, wsb), dtype=torch.uint8, device=dev)
+        sums = torch.empty(2, dtype=torch.float64, device=dev)
+        rowsum = torch.empty(A, dtype=torch.float64, device=dev) if want_dX else None
+        var, ls = float(self.variance.value), float(self.lengthscales.value)
+        h.call("rvgp_rbf_adjoint_f64", int(A), int(B), Gbar, I64(Gbar.stride(0)), Pm, I64(Pm.stride(0)), xa2, xb2, var, ls,
+               Pm if want_dX else None, I64(Pm.stride(0)), rowsum, sums, ws, I64(wsb))
+        sh = sums.cpu().numpy()
+        grads = {"variance": float(sh[0] / var), "lengthscales": float(sh[1] / ls)}
+        if not want_dX:
+            return grads, None
+        HX = torch.empty((A, k), dtype=torch.float64, device=dev)
+        split, sws = _splitk(B, A * k, dev)
+        _dgemm(h, A, k, B, Pm, Pm.stride(0), 1, XB, XB.stride(0), 0, HX, HX.stride(0), split_k=split, ws=sws)   # H XB
+        dX = torch.empty((A, k), dtype=torch.float64, device=dev)
+        h.call("rvgp_rbf_dx_f64", I64(A), int(k), HX, I64(HX.stride(0)), rowsum, XA, I64(XA.stride(0)), ls, dX,
+               I64(dX.stride(0)))
+        return grads, dX
+
+    def _diag_adjoint_uniform(self, X, g, cache):
+        return {"variance": float(g * X.shape[0]), "lengthscales": 0.0}

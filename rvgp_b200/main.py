@@ -1,6 +1,8 @@
-"""Mirror of the reference's ``RVGP/main.py``: ``train_gp`` (exported as ``RVGP.fit``), ``optimize_model_with_scipy``
-and ``manifold_GPR`` with ``transform`` / ``predict_f`` -- same names, argument meaning, prints and quirks
-(main.py:11-137), GPflow/TensorFlow replaced by rvgp_b200.gp.DeviceGPR.
+"""Mirror of the reference's ``RVGP/main.py``: ``train_gp`` (exported as ``RVGP.fit``), ``optimize_model_with_scipy``,
+``manifold_GPR`` and ``manifold_SGPR`` with ``transform`` / ``predict_f`` -- same names, argument meaning, prints and
+quirks (main.py:11-137), GPflow/TensorFlow replaced by rvgp_b200.gp.DeviceGPR (spectral
+kernel, rank-k / dense), rvgp_b200.gp_general.DenseGPR (``kernel='rbf'``, main.py:33-37) and
+rvgp_b200.gp_general.DeviceSGPR (``n_inducing_points``, main.py:59-67,119-137).
 
 Reproduced on purpose (parity beats intent):
   * ``noise_variance`` is accepted and DROPPED: the likelihood variance starts at GPflow's default 1.0 and is
@@ -20,7 +22,8 @@ from . import params as P
 from .geometry import furthest_point_sampling, gather_rows_device, to_device_f64  # noqa: F401
 from ._cabi import RvgpError
 from .gp import DeviceGPR
-from .kernels import ManifoldKernel
+from .gp_general import DenseGPR, DeviceSGPR
+from .kernels import ManifoldKernel, RBF
 
 
 class _Gaussian:
@@ -51,17 +54,17 @@ def _as_node_indices(test_ind, n):
     return a.reshape(-1).astype(np.int64)
 
 
-class manifold_GPR:
-    """GP regression model (replaces gpflow.models.GPR subclass, main.py:98-116)."""
+def _rows_of(data, name, node_ind):
+    """``getattr(data, name).reshape(n, -1)[node_ind]`` on the device: (len(node_ind), cols) float64."""
+    A = data.device_array(name)
+    idx = torch.from_numpy(np.ascontiguousarray(node_ind, dtype=np.int64)).to(A.device)
+    return A.reshape(data.n, -1).index_select(0, idx).contiguous()
 
-    def __init__(self, data, kernel, mean_function=None, noise_variance=None, likelihood=None, solver="auto"):
-        # like the reference, mean_function / noise_variance / likelihood are ignored (main.py:100)
-        X, Y = data
-        self.data = (to_device_f64(X), to_device_f64(Y))
-        self.kernel = kernel
-        self.likelihood = _Gaussian()
-        self._gpr = DeviceGPR(self.data[0], self.data[1], solver=solver)
-        self.solver = self._gpr.solver
+
+class _Model:
+    """What manifold_GPR and manifold_SGPR share: parameters, the L-BFGS-B objective, ``transform``."""
+
+    inducing = None          # SGPR: DeviceSGPR (its Z is trained with the hyper-parameters, GPflow's default)
 
     @property
     def trainable_parameters(self):
@@ -70,42 +73,44 @@ class manifold_GPR:
             ps.append(self.likelihood.variance)
         return ps
 
-    def log_marginal_likelihood(self):
-        S = self.kernel.eval_S(typ=self.kernel.typ)
-        return self._gpr.lml_and_grads(S, self.likelihood.variance.value, grads=False)
-
     def training_loss(self):
-        return -self.log_marginal_likelihood()
+        return -self.maximum_log_likelihood_objective()
 
-    def _loss_and_grad(self, u, plist):
-        for p, ui in zip(plist, u):
+    # ---- variables as one host vector: [unconstrained scalars..., Z.ravel()] -------------------------------------
+    def _pack(self, plist):
+        u = np.array([p.unconstrained for p in plist], dtype=np.float64)
+        if self.inducing is not None:
+            u = np.concatenate([u, self.inducing.Z.cpu().numpy().ravel()])
+        return u
+
+    def _unpack(self, v, plist):
+        for p, ui in zip(plist, v[:len(plist)]):
             p.unconstrained = float(ui)
+        if self.inducing is not None:
+            Z = torch.from_numpy(np.ascontiguousarray(v[len(plist):]).reshape(tuple(self.inducing.Z.shape)))
+            self.inducing.Z.copy_(Z)
+
+    def _loss_and_grad(self, v, plist):
+        v = np.asarray(v, dtype=np.float64)
+        self._unpack(v, plist)
         try:
             with np.errstate(all="ignore"):
-                S, dS = self.kernel.eval_S(typ=self.kernel.typ, grads=True)
-                if not np.all(np.isfinite(S)) or np.any(S <= 0):
-                    raise FloatingPointError("non-finite spectral density")
-                lml, gS, gnoise = self._gpr.lml_and_grads(S, self.likelihood.variance.value, grads=True)
-                if not (np.isfinite(lml) and np.all(np.isfinite(gS)) and np.isfinite(gnoise)):
-                    raise FloatingPointError("non-finite LML")
+                f, kgrads, gnoise, dZ = self._evaluate()
+                vals = list(kgrads.values()) + [gnoise, f]
+                if not np.all(np.isfinite(vals)):
+                    raise FloatingPointError("non-finite objective")
         except (FloatingPointError, RvgpError):
             # a trial point of the line search left the domain (non-finite density / non-SPD Gram): report a huge
             # loss so L-BFGS-B backs off (TensorFlow would raise here and abort the fit)
-            return 1e50, np.zeros(len(plist))
+            return 1e50, np.zeros(len(v))
         g = []
         for p in plist:
-            if p is self.likelihood.variance:
-                d = gnoise
-            else:
-                d = float(gS @ dS[p.name])
+            d = gnoise if p is self.likelihood.variance else kgrads[p.name]
             g.append(-d * p.transform.dforward(p.unconstrained))
-        return -lml, np.array(g)
-
-    def predict_f(self, Xnew, full_cov=False):
-        """(mean (N*,1), variance (N*,1)) as CUDA tensors with a ``.numpy()``-like host path via .cpu()."""
-        S = self.kernel.eval_S(typ=self.kernel.typ)
-        mean, var = self._gpr.predict(S, self.likelihood.variance.value, to_device_f64(Xnew))
-        return _HostView(mean), _HostView(var)
+        g = np.array(g, dtype=np.float64)
+        if dZ is not None:
+            g = np.concatenate([g, -dZ.cpu().numpy().ravel()])
+        return -f, g
 
     def transform(self, data, test_ind, as_device=False):
         first = test_ind[0]
@@ -113,6 +118,7 @@ class manifold_GPR:
             test_x = to_device_f64(np.asarray(test_ind))                 # positional encodings given directly (main.py:108-109)
             n_out = test_x.shape[0]
         else:
+            # like the reference, ALWAYS rows of evecs_Lc (main.py:104-106), whatever the kernel was trained on
             nodes = _as_node_indices(test_ind, data.n)
             test_x = _node_rows_device(data, nodes)
             n_out = len(nodes)
@@ -122,6 +128,82 @@ class manifold_GPR:
         f_pred_mean = f_pred_mean.numpy().reshape(n_out, -1)
         f_pred_std = f_pred_std.numpy().reshape(n_out, -1)
         return f_pred_mean, f_pred_std
+
+
+class manifold_GPR(_Model):
+    """GP regression model (replaces the gpflow.models.GPR subclass, main.py:98-116)."""
+
+    def __init__(self, data, kernel, mean_function=None, noise_variance=None, likelihood=None, solver="auto"):
+        # like the reference, mean_function / noise_variance / likelihood are ignored (main.py:100)
+        X, Y = data
+        self.data = (to_device_f64(X), to_device_f64(Y))
+        self.kernel = kernel
+        self.likelihood = _Gaussian()
+        self._spectral = isinstance(kernel, ManifoldKernel) and self.data[1].shape[1] == 1 and solver != "general"
+        if self._spectral:
+            self._gpr = DeviceGPR(self.data[0], self.data[1], solver=solver)
+            self.solver = self._gpr.solver
+        else:
+            self._gpr = DenseGPR(self.data[0], self.data[1], kernel)
+            self.solver = "general"
+
+    def log_marginal_likelihood(self):
+        if self._spectral:
+            S = self.kernel.eval_S(typ=self.kernel.typ)
+            return self._gpr.lml_and_grads(S, self.likelihood.variance.value, grads=False)
+        return self._gpr.lml_and_grads(self.likelihood.variance.value, grads=False)
+
+    maximum_log_likelihood_objective = log_marginal_likelihood
+
+    def _evaluate(self):
+        if self._spectral:
+            S = self.kernel.eval_S(typ=self.kernel.typ)
+            if not np.all(np.isfinite(S)) or np.any(S <= 0):
+                raise FloatingPointError("non-finite spectral density")
+            lml, gS, gnoise = self._gpr.lml_and_grads(S, self.likelihood.variance.value, grads=True)
+            if not np.all(np.isfinite(gS)):
+                raise FloatingPointError("non-finite LML gradient")
+            return lml, self.kernel._chain(gS), gnoise, None
+        lml, kgrads, gnoise = self._gpr.lml_and_grads(self.likelihood.variance.value, grads=True)
+        return lml, kgrads, gnoise, None
+
+    def predict_f(self, Xnew, full_cov=False):
+        """(mean (N*,R), variance (N*,R)) as CUDA tensors with a ``.numpy()``-like host path via .cpu()."""
+        if self._spectral:
+            S = self.kernel.eval_S(typ=self.kernel.typ)
+            mean, var = self._gpr.predict(S, self.likelihood.variance.value, to_device_f64(Xnew))
+        else:
+            mean, var = self._gpr.predict(self.likelihood.variance.value, to_device_f64(Xnew))
+        return _HostView(mean), _HostView(var)
+
+
+class manifold_SGPR(_Model):
+    """Sparse GP regression (replaces the gpflow.models.SGPR subclass, main.py:119-137): Titsias' collapsed bound with
+    trainable inducing points; like the reference, mean_function / noise_variance / likelihood are ignored (:121)."""
+
+    def __init__(self, data, kernel, inducing_variable, mean_function=None, noise_variance=None, likelihood=None):
+        X, Y = data
+        self.data = (to_device_f64(X), to_device_f64(Y))
+        self.kernel = kernel
+        self.likelihood = _Gaussian()
+        self.inducing = DeviceSGPR(self.data[0], self.data[1], to_device_f64(inducing_variable), kernel)
+        self.solver = "sgpr"
+
+    @property
+    def inducing_variable(self):
+        return _HostView(self.inducing.Z)
+
+    def elbo(self):
+        return self.inducing.elbo_and_grads(self.likelihood.variance.value, grads=False)
+
+    maximum_log_likelihood_objective = elbo
+
+    def _evaluate(self):
+        return self.inducing.elbo_and_grads(self.likelihood.variance.value, grads=True)
+
+    def predict_f(self, Xnew, full_cov=False):
+        mean, var = self.inducing.predict(self.likelihood.variance.value, to_device_f64(Xnew))
+        return _HostView(mean), _HostView(var)
 
 
 class _HostView:
@@ -145,13 +227,12 @@ def optimize_model_with_scipy(model, epochs):
     options={"disp": True, "maxiter": epochs})  (main.py:87-95).  4 scalars on the host; every evaluation's
     linear algebra on the device."""
     plist = model.trainable_parameters
-    if not plist:
+    if not plist and model.inducing is None:
         return model
-    u0 = np.array([p.unconstrained for p in plist])
+    u0 = model._pack(plist)
     res = scipy.optimize.minimize(lambda u: model._loss_and_grad(u, plist), u0, jac=True, method="L-BFGS-B",
                                   options={"maxiter": epochs})
-    for p, ui in zip(plist, res.x):
-        p.unconstrained = float(ui)
+    model._unpack(res.x, plist)
     model.opt_result = res
     return model
 
@@ -173,30 +254,42 @@ def train_gp(data,
         train_ind = np.arange(data.n)
     train_nodes = _as_node_indices(train_ind, data.n)
 
-    if kernel == 'rbf':
-        raise NotImplementedError("kernel='rbf' (channel-wise baseline on evecs_L) is a 'next' row (SURVEY.md 8f)")
-    if n_inducing_points is not None:
-        raise NotImplementedError("SGPR / inducing points is a 'next' row (SURVEY.md 8f)")
-
     vec = data._duals["vectors"].get_dev(data.device) if hasattr(data, "_duals") else to_device_f64(data.vectors)
-    dim = vec.shape[1]
+    vd = vec.reshape(data.n, -1)
+    feature = "evecs_Lc"
+    dim = vd.shape[1]
     if kernel is None:
         kernel = ManifoldKernel(data, nu=3 / 2, kappa=5, typ='matern', sigma_f=1.)
+    if isinstance(kernel, str) and kernel == 'rbf':
+        kernel = RBF()
+        feature = "evecs_L"                 # main.py:35: rows of the SCALAR Laplacian's eigenvectors, one row per node
+        dim = 1
+        print('Using RBF kernel, treating vectors channel-wise.')
 
     # split training and test set: sklearn on an index array gives the same rows as splitting the arrays
     # (main.py:40-45); bit-exact host RNG, only indices go to the GPU
     tr, te = train_test_split(np.arange(len(train_nodes)), test_size=test_size, random_state=seed)
-    in_train = _node_rows_device(data, train_nodes[tr])
-    in_test = _node_rows_device(data, train_nodes[te])
-    vd = vec.reshape(data.n, dim)
+    if feature == "evecs_Lc":
+        in_train = _node_rows_device(data, train_nodes[tr])             # (n_tr * D, k)
+        in_test = _node_rows_device(data, train_nodes[te])
+    else:
+        in_train = _rows_of(data, "evecs_L", train_nodes[tr])           # (n_tr, k_L)
+        in_test = _rows_of(data, "evecs_L", train_nodes[te])
     idx_tr = torch.from_numpy(train_nodes[tr]).to(vd.device)
     idx_te = torch.from_numpy(train_nodes[te]).to(vd.device)
-    out_train = vd.index_select(0, idx_tr).reshape(-1, 1)
-    out_test = vd.index_select(0, idx_te).reshape(-1, 1)
+    out_train = vd.index_select(0, idx_tr).reshape(len(tr) * dim, -1)
+    out_test = vd.index_select(0, idx_te).reshape(len(te) * dim, -1)
 
     P.set_default_positive_minimum(positivity_constraint)
 
-    GP = manifold_GPR((in_train, out_train), kernel, noise_variance=noise_variance, solver=solver)
+    if n_inducing_points is None:
+        GP = manifold_GPR((in_train, out_train), kernel, noise_variance=noise_variance, solver=solver)
+    else:
+        # inducing points: furthest-point sampling in FEATURE space (main.py:60-61), on the device (K1, D = k)
+        from .fps import furthest_point_sampling_device
+        ind, _ = furthest_point_sampling_device(in_train, N=int(n_inducing_points))
+        inducing_variable = in_train.index_select(0, ind.to(torch.int64))
+        GP = manifold_SGPR((in_train, out_train), kernel, inducing_variable, noise_variance=noise_variance)
 
     if kernel_variance is not None:
         kernel.variance.assign(kernel_variance)          # AttributeError for ManifoldKernel, as in the reference

@@ -341,6 +341,29 @@ int rvgp_rbf_dx_f64(rvgp_handle_t h, int64_t m, int k, const double* HX, int64_t
                     const double* XA, int64_t ldx, double lengthscale, double* out, int64_t ldo);
 int rvgp_scale_shift_f64(rvgp_handle_t h, int64_t nrows, int ncols, double alpha, double beta, double* A, int64_t lda);
 
+/* ---- K19: divergence / curl features of a vector field on a 3-D point cloud (examples/eeg_example/eeg_utils.py:46-80,
+ * compute_vectorfield_features).  knn (n x k, int32): neighbour lists from rvgp_knn_f64 / rvgp_knn_grid_f64
+ * (self excluded, ascending distance = KDTree.query order).  ref_row0 = 1 reproduces the reference's use of
+ * normalized_vectors[0] as the subtracted vector (eeg_utils.py:67); 0 subtracts the point's own vector.
+ * div (n), curl (n x 3); both averaged over the k neighbours. */
+int rvgp_vectorfield_features_f64(rvgp_handle_t h, int n, int k, const double* positions, const double* vectors,
+                                  const int32_t* knn, int ref_row0, double* div, double* curl);
+
+/* ---- K20: consistent orientation of d = 2 gauges -> complex-Hermitian form of the connection Laplacian (no reference
+ * counterpart; the eigenpairs of D Lc D, D = diag(1, s_i), are those of Lc = compute_connection_laplacian, geometry.py:14-52,
+ * up to the sign flip D, and every eigenvalue is exactly double -- the pairs eigsh returns at geometry.py:73).
+ * rvgp_orient_steps: `steps` sweeps of pull-style label propagation over the block-CSR pattern; labels (n, int32): 0 =
+ *   unlabelled, +-1 = node sign; seed at least one node before the first call; *changed is set when any label was written.
+ * rvgp_orient_check: out2[0] = number of stored off-diagonal blocks with s_i s_j det(block) < 0, out2[1] = unlabelled nodes.
+ * rvgp_rot90_nodes_f64: out = J V, (J V)[2i] = -V[2i+1], (J V)[2i+1] = V[2i] (out must not alias V).
+ * rvgp_flip_odd_rows_f64: V[2i+1, :] *= s[i] (apply D to a block vector, or to the second gauge coordinate). */
+int rvgp_orient_steps(rvgp_handle_t h, int n, const int32_t* indptr, const int32_t* indices, const double* vals,
+                      int32_t* labels, int32_t* changed, int steps);
+int rvgp_orient_check(rvgp_handle_t h, int n, const int32_t* indptr, const int32_t* indices, const double* vals,
+                      const int32_t* labels, int32_t* out2);
+int rvgp_rot90_nodes_f64(rvgp_handle_t h, int64_t nnodes, int ncols, const double* V, int64_t ldv, double* out, int64_t ldo);
+int rvgp_flip_odd_rows_f64(rvgp_handle_t h, int64_t nnodes, int ncols, const int32_t* s, double* V, int64_t ldv);
+
 #ifdef __cplusplus
 }
 #endif

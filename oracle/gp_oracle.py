@@ -373,7 +373,7 @@ def sgpr_elbo(kern, p, X, Y, Z, noise, grads=False):
     bound = float(bound)
     if not grads:
         return bound
-    # reverse mode by hand (DESIGN.md section 9): with t = LB^-T c, gamma = L^-T t, beta = (Y - Kfu gamma) / noise,
+    # reverse mode by hand (DESIGN.md section 8): with t = LB^-T c, gamma = L^-T t, beta = (Y - Kfu gamma) / noise,
     #   dF/dKuf = L^-T [ t beta^T + (R / sigma) (I - B^-1) A ],  dF/dKuu = L^-T [ -1/2 t t^T - R/2 (B - 2I + B^-1) ] L^-1,
     #   dF/dKdiag = -R / (2 noise)
     t = scipy.linalg.solve_triangular(LB, c, lower=True, trans="T")

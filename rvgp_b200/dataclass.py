@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import geometry as geo
-from .eigensolver import BsrMatrix, smallest_eigenpairs
+from .eigensolver import BsrMatrix, smallest_eigenpairs, smallest_eigenpairs_paired
 from .smoothing import vector_diffusion_device
 
 
@@ -145,14 +145,27 @@ class data:
         # K9 v4: the Chebyshev filter of the d = 2 connection Laplacian runs on the FP64-MMA row-group kernel
         # (0.65 vs 0.48 of HBM peak at C4 size; DESIGN.md K9 log).  RVGP_SPMM_MMA=0 keeps the gather kernel.
         self.stats["spmm_mma"] = False
-        if dim_man == 2 and not shard and n >= 64 and os.environ.get("RVGP_SPMM_MMA", "1") != "0":
-            self.stats["spmm_mma"] = A_Lc.enable_mma() is not None
-        self.timings["connections"] = tick() - t0
-
-        say('Compute eigendecompositions')
         N_L, N_Lc = n, n * dim_man
         k_L = N_L if (n_eigenpairs is None or n_eigenpairs >= N_L) else n_eigenpairs
         k_Lc = N_Lc if (n_eigenpairs is None or n_eigenpairs >= N_Lc) else n_eigenpairs
+        # K20: on an orientable surface (d = 2) the gauges can be re-oriented so that every block of Lc is a scaled rotation;
+        # the eigensolver then works on the n x n complex-Hermitian form with HALF the columns (eigensolver.py, paired mode).
+        # The re-oriented frames are internal: d.gauges, d.Lc and the local-coordinate eigenvectors keep the reference's signs.
+        self.stats["paired"] = False
+        A_eig, gauges_eig, orient = A_Lc, gauges_p, None
+        if (dim_man == 2 and n >= 64 and 8 * k_Lc <= N_Lc and os.environ.get("RVGP_PAIRED", "1") != "0"):
+            orient = geo.orient_gauges_device(p_indptr, p_indices, Lc_vals_p)
+            if orient is not None:
+                gauges_eig = gauges_p.clone()
+                gauges_eig[:, :, 1] *= orient.to(torch.float64)[:, None]
+                A_eig = BsrMatrix(n, dim_man, p_indptr, p_indices, geo.connections_device(gauges_eig, p_indptr, p_indices))
+                self.stats["paired"] = True
+        eig_Lc = smallest_eigenpairs_paired if self.stats["paired"] else smallest_eigenpairs
+        if dim_man == 2 and not shard and n >= 64 and os.environ.get("RVGP_SPMM_MMA", "1") != "0":
+            self.stats["spmm_mma"] = A_eig.enable_mma() is not None
+        self.timings["connections"] = tick() - t0
+
+        say('Compute eigendecompositions')
         hi = 2.0 * (max_row - 1)
         t0 = tick()
         st_L, st_Lc = {}, {}
@@ -163,7 +176,7 @@ class data:
             plan = HaloPlan(p_indptr, p_indices, bounds, rank)
             plan.exchange_requests()
             S_L = ShardedBsr(plan, 1, None, comm)
-            S_Lc = ShardedBsr(plan, dim_man, plan.local_values(Lc_vals_p), comm)
+            S_Lc = ShardedBsr(plan, dim_man, plan.local_values(A_eig.vals), comm)
             if dim_man == 2 and os.environ.get("RVGP_SPMM_MMA", "1") != "0" and os.environ.get("RVGP_PEER_HALO", "1") != "0":
                 self.stats["spmm_mma"] = S_Lc.enable_mma() is not None
             counts = [int(bounds[r + 1] - bounds[r]) for r in range(world)]
@@ -174,14 +187,14 @@ class data:
             t0 = tick()
             r0, r1 = plan.r0, plan.r1
 
-            def lc_guess_loc(V, U=U_L_p[r0:r1], G=gauges_p[r0:r1].contiguous()):
+            def lc_guess_loc(V, U=U_L_p[r0:r1], G=gauges_eig[r0:r1].contiguous()):
                 hh = geo.get_handle(dev.index)
                 ncols = min(V.shape[1], U.shape[1] * D)
                 hh.call("rvgp_lift_guess", G, geo.I64(r1 - r0), int(D), int(dim_man), U, geo.I64(U.stride(0)),
                         int(U.shape[1]), V, geo.I64(V.stride(0)), int(ncols))
 
-            evals_Lc, U_loc = smallest_eigenpairs(S_Lc, k_Lc, upper_bound=hi, tol=eig_tol, stats=st_Lc, comm=comm,
-                                                  init_fn=lc_guess_loc if warm_start else None)
+            evals_Lc, U_loc = eig_Lc(S_Lc, k_Lc, upper_bound=hi, tol=eig_tol, stats=st_Lc, comm=comm,
+                                     init_fn=lc_guess_loc if warm_start else None)
             U_Lc_p = comm.allgather_rows(U_loc, [c * dim_man for c in counts])
             del U_loc
             self.timings["eig_Lc"] = tick() - t0
@@ -193,13 +206,19 @@ class data:
                 # smooth vector fields ~ scalar eigenfunctions x projected constant ambient directions
                 hh = geo.get_handle(dev.index)
                 ncols = min(V.shape[1], U.shape[1] * D)
-                hh.call("rvgp_lift_guess", gauges_p, geo.I64(n), int(D), int(dim_man), U, geo.I64(U.stride(0)),
+                hh.call("rvgp_lift_guess", gauges_eig, geo.I64(n), int(D), int(dim_man), U, geo.I64(U.stride(0)),
                         int(U.shape[1]), V, geo.I64(V.stride(0)), int(ncols))
 
-            evals_Lc, U_Lc_p = smallest_eigenpairs(A_Lc, k_Lc, upper_bound=hi, tol=eig_tol, stats=st_Lc,
-                                                   init_fn=lc_guess if warm_start else None)
+            evals_Lc, U_Lc_p = eig_Lc(A_eig, k_Lc, upper_bound=hi, tol=eig_tol, stats=st_Lc,
+                                      init_fn=lc_guess if warm_start else None)
             self.timings["eig_Lc"] = tick() - t0
         self.stats["eig_L"], self.stats["eig_Lc"] = st_L, st_Lc
+        if self.stats["paired"]:
+            # back to the reference's frame signs: v = D v', D = diag(1, s_i) (Lc = D Lc' D)
+            U_Lc_p = U_Lc_p.contiguous()
+            geo.get_handle(dev.index).call("rvgp_flip_odd_rows_f64", geo.I64(n), int(U_Lc_p.shape[1]), orient, U_Lc_p,
+                                           geo.I64(U_Lc_p.stride(0)))
+            del A_eig, gauges_eig
 
         t0 = tick()
         # un-permute; scale by sqrt(#rows) (geometry.py:75); lift T u to ambient coordinates (dataclass.py:57-59)

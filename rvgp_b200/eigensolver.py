@@ -583,3 +583,211 @@ def _next_degrees(theta, res, k, tol_abs, a_cut, hi, lo_spec, cond_max, deg_cap=
     if k < len(d):
         d[k:] = np.minimum(d[k:], d[:k].max())
     return np.minimum(d, deg_cap).astype(np.int64)
+
+
+# =====================================================================================================================
+# Paired mode: d = 2 connection Laplacian whose blocks are ALL scaled rotations (after geometry.orient_gauges_device).
+# Such a matrix commutes with the per-node quarter turn J, i.e. it is an n x n complex-Hermitian operator on
+# z_i = x_i + i y_i (real storage unchanged: column c of a (2n x b) block IS one complex vector).  Every eigenvalue is an
+# exactly double eigenvalue of the real matrix (eigenvectors v and J v), so the block method needs HALF the columns:
+#   filter            unchanged (the SpMM is complex-linear as it stands), on b/2 columns
+#   Gram  V^H W       = V^T W + i (J V)^T W        two real lower-triangle Grams of half the width  (1/2 the flops)
+#   apply V C         = V Re(C) + (J V) Im(C)      two real dgemms of half the width                  (1/2 the flops)
+#   projected problem   complex Hermitian (m/2) x (m/2) on the host (LAPACK zheevd / zpotrf), as in the real mode
+# The caller expands the result: eigenvalue theta_j -> (theta_j, theta_j), eigenvectors (v_j, J v_j).
+# =====================================================================================================================
+def _herm_from_lower(Gr_d, Gi_d):
+    """Complex Hermitian matrix from the lower-triangle tiles of its real (symmetric) and imaginary (antisymmetric) parts."""
+    Gr = np.tril(Gr_d.cpu().numpy())
+    Gr = Gr + np.tril(Gr, -1).T
+    Gi = np.tril(Gi_d.cpu().numpy(), -1)
+    Gi = Gi - Gi.T
+    return Gr + 1j * Gi
+
+
+def _chol_upper_shifted_c(G):
+    """Complex version of _chol_upper_shifted: R upper with G = R^H R."""
+    try:
+        return np.linalg.cholesky(G).conj().T, False
+    except np.linalg.LinAlgError:
+        pass
+    m = G.shape[0]
+    shift = 1e-13 * m
+    while True:
+        try:
+            return np.linalg.cholesky(G + shift * np.eye(m)).conj().T, True
+        except np.linalg.LinAlgError:
+            shift *= 100.0
+            if shift > 1.0:
+                raise
+
+
+def smallest_eigenpairs_paired(A, k, upper_bound, lower_bound=0.0, tol=1e-12, nex=None, seed=0, max_outer=80,
+                               cond_max=1e6, deg0=20, panel=None, stats=None, verbose=False, comm=None,
+                               refine_bound=True, init_fn=None):
+    """Smallest k eigenpairs of a d = 2 block matrix ``A`` that commutes with J (all blocks scaled rotations), through its
+    complex-Hermitian form.  Same contract as ``smallest_eigenpairs``: returns (evals (k,), evecs (N, k)) with unit-norm
+    columns, ascending; columns 2j and 2j+1 are (v_j, J v_j) of the j-th complex eigenpair."""
+    dev = A.indptr.device
+    h = get_handle(dev.index)
+    assert A.d == 2
+    N = A.nrows                       # LOCAL real rows
+    nn = N // 2                       # local nodes
+    Nglob = N
+    if comm is not None and comm.world > 1:
+        t = torch.tensor([N], dtype=torch.int64, device=dev)
+        comm.allreduce_(t)
+        Nglob = int(t.item())
+    else:
+        comm = None
+    nglob = Nglob // 2                # dimension of the complex problem
+    k = int(min(k, Nglob))
+    kc = (k + 1) // 2
+    nexc = max(8, int(math.ceil(0.2 * kc))) if nex is None else max(1, (int(nex) + 1) // 2)
+    mc = min(nglob, kc + nexc)
+    if panel is None:
+        panel = 64 if mc >= 128 else 32
+    if mc < nglob:
+        mc = min(nglob, ((mc + panel - 1) // panel) * panel)
+    hi = float(upper_bound)
+    if refine_bound and Nglob > 8 * mc:
+        hi = min(hi, 1.01 * lanczos_upper_bound(A, comm=comm, h=h))
+    lo_spec = float(lower_bound)
+    tol_abs = tol * float(upper_bound)
+    st = stats if stats is not None else {}
+    st.update(dict(N=N, k=k, m=mc, paired=True, panel=panel, spmm_launches=0, filter_launches=0, filter_col_degrees=0,
+                   outer=0, t_filter=0.0, t_dense=0.0, t_host=0.0, spmm_bytes_fused=int(A.spmm_bytes(panel, fused=True)),
+                   spmm_bytes_plain=int(A.spmm_bytes(panel, fused=False)), d=A.d, world=(comm.world if comm else 1),
+                   hi=hi, hi_gershgorin=float(upper_bound)))
+
+    B1 = torch.empty((N, mc), dtype=torch.float64, device=dev)
+    B2 = torch.empty((N, mc), dtype=torch.float64, device=dev)
+    JV = torch.empty((N, mc), dtype=torch.float64, device=dev)
+    w0 = torch.empty((N, panel), dtype=torch.float64, device=dev)
+    w1 = torch.empty((N, panel), dtype=torch.float64, device=dev)
+    w2 = None
+    if isinstance(A, BsrMatrix) and A.mma is not None:
+        w2 = torch.empty((N, panel), dtype=torch.float64, device=dev)
+    st["spmm_kernel"] = "mma_native" if w2 is not None else "gather"
+    Gr = torch.empty((mc, mc), dtype=torch.float64, device=dev)
+    Gi = torch.empty((mc, mc), dtype=torch.float64, device=dev)
+    Hr = torch.empty((mc, mc), dtype=torch.float64, device=dev)
+    Hi = torch.empty((mc, mc), dtype=torch.float64, device=dev)
+    Cr = torch.empty((mc, mc), dtype=torch.float64, device=dev)
+    Ci = torch.empty((mc, mc), dtype=torch.float64, device=dev)
+    theta_d = torch.empty(mc, dtype=torch.float64, device=dev)
+    dense = _Dense(h, N, mc, dev, comm)
+
+    def rot90(X, out):
+        h.call("rvgp_rot90_nodes_f64", I64(nn), int(X.shape[1]), X, I64(X.stride(0)), out, I64(out.stride(0)))
+        return out
+
+    def gram_c(X, JX, Y, outr, outi):
+        """X^H Y (Hermitian expected): lower tiles of X^T Y and (J X)^T Y."""
+        outr.zero_(); outi.zero_()
+        dense.gram(X, Y, outr, sym=True)
+        dense.gram(JX, Y, outi, sym=True)
+        return _herm_from_lower(outr, outi)
+
+    def apply_c(X, JX, Cm, out):
+        """out = X Cm for a complex (mc x mc) host matrix: X Re(Cm) + (J X) Im(Cm)."""
+        Cr.copy_(torch.from_numpy(np.ascontiguousarray(Cm.real)))
+        Ci.copy_(torch.from_numpy(np.ascontiguousarray(Cm.imag)))
+        dense.apply(X, Cr, out)
+        h.call("rvgp_dgemm_acc_f64", int(N), int(mc), I64(mc), 1.0, JX, I64(JX.stride(0)), 1, Ci, I64(Ci.stride(0)), 0, 1.0,
+               out, I64(out.stride(0)))
+        return out
+
+    V, W = B1, B2
+    h.call("rvgp_fill_uniform_f64", I64(N), int(mc), V, I64(V.stride(0)), U64(seed), I64(0), I64(A.row_offset))
+    if init_fn is not None:
+        init_fn(V)
+
+    deg = np.full(mc, deg0, dtype=np.int64)
+    a_cut = lo_spec + 0.3 * (hi - lo_spec)
+    theta = res = None
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    ev2 = torch.cuda.Event(enable_timing=True)
+
+    for it in range(max_outer):
+        ev0.record()
+        for p0 in range(0, mc, panel):
+            p1 = min(mc, p0 + panel)
+            dg = int(deg[p0:p1].max())
+            if dg <= 0:
+                continue
+            if w2 is not None and p1 - p0 == panel:
+                A.cheb_filter(V[:, p0:p1], w0, w1, p1 - p0, dg, lo_spec, float(a_cut), hi, h=h, w2=w2)
+            else:
+                A.cheb_filter(V[:, p0:p1], w0, w1, p1 - p0, dg, lo_spec, float(a_cut), hi, h=h)
+            st["spmm_launches"] += dg
+            st["filter_launches"] += dg
+            st["filter_col_degrees"] += dg * (p1 - p0)
+        ev1.record()
+        # ---- complex CholeskyQR (shifted CholeskyQR3 on breakdown), then Rayleigh-Ritz ---------------------------------
+        for _pass in range(4):
+            nrm = dense.coldot(V, V)
+            inv = torch.rsqrt(nrm)
+            dense.colscale(V, inv)
+            rot90(V, JV)
+            G = gram_c(V, JV, V, Gr, Gi)
+            t0 = time.perf_counter()
+            R, shifted = _chol_upper_shifted_c(G)
+            Rinv = _tri_inv_upper(R)
+            st["t_host"] += time.perf_counter() - t0
+            apply_c(V, JV, Rinv, W)
+            V, W = W, V
+            st["cholqr_passes"] = st.get("cholqr_passes", 0) + 1
+            if not shifted:
+                break
+        rot90(V, JV)
+        A.matmat(V, out=W, h=h)                            # W = A V
+        st["spmm_launches"] += math.ceil(mc / 64)
+        G = gram_c(V, JV, V, Gr, Gi)
+        Hm = gram_c(V, JV, W, Hr, Hi)                      # V^H A V
+        t0 = time.perf_counter()
+        R2 = np.linalg.cholesky(G).conj().T
+        R2inv = _tri_inv_upper(R2)
+        Hm = R2inv.conj().T @ Hm @ R2inv
+        Hm = 0.5 * (Hm + Hm.conj().T)
+        theta, Y = np.linalg.eigh(Hm)
+        Cm = R2inv @ Y
+        st["t_host"] += time.perf_counter() - t0
+        theta_d.copy_(torch.from_numpy(np.ascontiguousarray(theta)))
+        apply_c(V, JV, Cm, W)                              # Ritz vectors
+        V, W = W, V
+        A.matmat(V, out=W, h=h)                            # A * Ritz vectors, for true residuals
+        st["spmm_launches"] += math.ceil(mc / 64)
+        res = torch.sqrt(dense.resid_sq(W, V, theta_d)).cpu().numpy()
+        ev2.record()
+        torch.cuda.synchronize(dev)
+        st["t_filter"] += ev0.elapsed_time(ev1) * 1e-3
+        st["t_dense"] += ev1.elapsed_time(ev2) * 1e-3
+        st["outer"] = it + 1
+
+        nconv = int((res[:kc] <= tol_abs).sum())
+        a_cut = float(theta[-1]) if mc < nglob else a_cut
+        if verbose:
+            print("  [eig paired] it %d  cut=%.6g  conv=%d/%d  maxres=%.3e  theta_k=%.9g" %
+                  (it, a_cut, nconv, kc, res[:kc].max(), theta[kc - 1]))
+        if nconv == kc or mc >= nglob:
+            break
+        a_cut = max(a_cut, lo_spec + 1e-12 * (hi - lo_spec) + theta[kc - 1] * (1 + 1e-9))
+        deg = _next_degrees(theta, res, kc, tol_abs, a_cut, hi, lo_spec, cond_max)
+
+    if not isinstance(A, BsrMatrix) and hasattr(A, "spmm_kernel_name"):
+        st["spmm_kernel"] = A.spmm_kernel_name
+    st["residual_max"] = float(res[:kc].max())
+    st["converged"] = bool((res[:kc] <= tol_abs).all())
+    # expand every complex pair (theta_j, v_j) to the two real eigenpairs (theta_j, v_j), (theta_j, J v_j)
+    del W, B1, B2                                        # V keeps the buffer it points to
+    Vk = V[:, :kc]
+    rot90(Vk, JV[:, :kc])
+    evecs = torch.empty((N, 2 * kc), dtype=torch.float64, device=dev)
+    evecs[:, 0::2] = Vk
+    evecs[:, 1::2] = JV[:, :kc]
+    evals = theta_d[:kc].repeat_interleave(2)[:k].clone()
+    if 2 * kc != k:
+        evecs = evecs[:, :k].contiguous()
+    return evals, evecs

@@ -163,6 +163,32 @@ def connections_device(gauges, indptr, indices, want_R=False):
     return (Lc, R) if want_R else Lc
 
 
+def orient_gauges_device(indptr, indices, Lc_vals, rounds=64, steps_per_round=128):
+    """K20.  Node signs s_i = +-1 (int32 cuda) with s_i s_j det(block(i, j)) = +1 on every stored edge of the d = 2
+    connection Laplacian, or None when no such signs exist (non-orientable surface, or a noisy tangent plane that breaks a
+    cycle).  Label propagation over the block-CSR pattern, one seed per connected component; verified edge by edge."""
+    h = get_handle(indptr.device.index)
+    n = int(indptr.numel()) - 1
+    dev = indptr.device
+    labels = torch.zeros(n, dtype=torch.int32, device=dev)
+    changed = torch.zeros(1, dtype=torch.int32, device=dev)
+    out2 = torch.zeros(2, dtype=torch.int32, device=dev)
+    labels[0] = 1
+    for _ in range(rounds * 64):
+        changed.zero_()
+        h.call("rvgp_orient_steps", int(n), indptr, indices, Lc_vals, labels, changed, int(steps_per_round))
+        if int(changed.item()) != 0:
+            continue
+        h.call("rvgp_orient_check", int(n), indptr, indices, Lc_vals, labels, out2)
+        bad, unlabelled = [int(v) for v in out2.cpu().tolist()]
+        if unlabelled == 0:
+            return labels if bad == 0 else None
+        # another connected component: seed its first node
+        first = int(torch.nonzero(labels == 0)[0].item())
+        labels[first] = 1
+    return None
+
+
 def morton_order_device(Xd):
     h = get_handle(Xd.device.index)
     n, D = Xd.shape

@@ -6,7 +6,7 @@ SURVEY.md 8f rows 1 and 3 (the callers either side of the hot path):
   * ``DeviceSGPR`` -- gpflow.models.SGPR (Titsias' collapsed bound) as reached from ``train_gp(n_inducing_points=...)``
     (RVGP/main.py:59-67,119-137), inducing points trainable like GPflow's default.
 
-GPflow differentiates these with TensorFlow's reverse mode; here the adjoints are written out by hand (DESIGN.md section 9)
+GPflow differentiates these with TensorFlow's reverse mode; here the adjoints are written out by hand (DESIGN.md section 8)
 and every O(M^2), O(N Mu) and O(Mu^3) operation is a librvgp_b200.so kernel (K10 dgemm, K14 potrf/trsm, K13/K17 Gram +
 adjoint, column reductions).  The kernel object supplies ``_gram``, ``_diag``, ``_adjoint`` and ``_diag_adjoint_uniform``
 (rvgp_b200/kernels.py: ManifoldKernel, RBF).  Host side: scalars and the k-vector chain rule only.
@@ -176,7 +176,7 @@ class DeviceSGPR:
                  + 0.5 * sum_c2 - 0.5 * R * kdiag_sum / noise + 0.5 * R * trAAT)
         if not grads:
             return bound
-        # ---- reverse mode (DESIGN.md section 9) ---------------------------------------------------------------------
+        # ---- reverse mode (DESIGN.md section 8) ---------------------------------------------------------------------
         t = c.clone()
         chB.solve(t, 1)                                                      # t = LB^-T c
         Binv = _inverse_from_chol(chB, Mu, self.dev)

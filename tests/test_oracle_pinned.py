@@ -102,3 +102,13 @@ def test_full_pipeline_c1():
     assert o.dim_man == 2 and o.L.nnz == 24854 and o.Lc.nnz == 99416
     np.testing.assert_allclose(o.evals_Lc, g["evals_Lc"], rtol=1e-8)
     np.testing.assert_allclose(o.evals_L, g["evals_L"], rtol=1e-8, atol=2e-7)
+
+
+def test_vectorfield_features_oracle_pinned_to_reference():
+    """oracle.compute_vectorfield_features == the unmodified reference function (examples/eeg_example/eeg_utils.py:46-80,
+    golden vectors from tests/golden/make_golden_eeg.py), bit for bit."""
+    from tests.conftest import load_golden
+    g = load_golden("eeg_features")
+    for k in (5, 3):
+        div, curl = O.compute_vectorfield_features(g["positions"], g["vectors"], k=k)
+        assert np.array_equal(div, g["div_k%d" % k]) and np.array_equal(curl, g["curl_k%d" % k])

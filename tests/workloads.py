@@ -19,6 +19,11 @@ def make_cloud(kind, n, seed=0):
             X /= np.linalg.norm(X, axis=1, keepdims=True)
             out.append(X[X[:, 2] >= 0.1])
         return np.concatenate(out)[:n]
+    if kind == "moebius":                     # NON-orientable 2-manifold: no consistent gauge orientation exists
+        u = g.uniform(0, 2 * np.pi, n)
+        v = g.uniform(-0.4, 0.4, n)
+        return np.stack([(1 + 0.5 * v * np.cos(u / 2)) * np.cos(u), (1 + 0.5 * v * np.cos(u / 2)) * np.sin(u),
+                         0.5 * v * np.sin(u / 2)], 1)
     if kind == "flat3torus":                  # 3-manifold in R^6 (d=3 blocks)
         a = g.uniform(0, 2 * np.pi, (n, 3))
         return np.concatenate([np.cos(a), np.sin(a)], 1)[:, [0, 3, 1, 4, 2, 5]].copy()

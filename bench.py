@@ -33,6 +33,14 @@ WORKLOADS = {
 }
 
 
+
+def _rnd(b):
+    """3 decimals for ordinary floats, 3 significant digits for tiny ones (residuals)."""
+    if isinstance(b, float):
+        return round(b, 3) if (b == 0.0 or abs(b) >= 1e-2) else float("%.3g" % b)
+    return b
+
+
 def make_inputs(wl):
     from tests.workloads import make_cloud
     kind, n, k, _ = WORKLOADS[wl]
@@ -197,15 +205,18 @@ def run_b200(args):
         "data": "synthetic",
         "config": {"workload": WORKLOADS[wl][3], "n_points": n, "ambient_dim": D, "n_eigenpairs": k,
                    "n_neighbors": 10,
-                   "parallelism": ("kNN queries + eigensolver rows sharded x%d (halo send/recv + Gram all-reduce over NCCL), "
-                                   "rest replicated" % world) if sharded else "single GPU",
+                   "parallelism": ("kNN queries + eigensolver rows sharded x%d (halo exchange: %s; Gram all-reduce over NCCL), "
+                                   "rest replicated" % (world, "own kernels over NVLink peer memory" if "peer" in str(st.get("spmm_kernel"))
+                                                        else "NCCL all_to_all")) if sharded else "single GPU",
                    "l2_policy": "inputs larger than L2 (block vectors %.1f GB, matrix %.2f GB)" %
                                 (A.nrows * st["m"] * 8 / 1e9, A.spmm_bytes(0) / 1e9)},
         "e2e": {"value": round(ms_e2e / 1e3 / n_e2e, 4), "unit": "s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
         "stages_s": {a: round(b, 3) for a, b in d_last.timings.items()},
-        "eig_Lc": {a: (round(b, 3) if isinstance(b, float) else b) for a, b in st.items()},
+        "eig_Lc": {a: _rnd(b) for a, b in st.items()},
+        "eig_L": {a: _rnd(b) for a, b in d_last.stats["eig_L"].items()},
+        "paired": bool(d_last.stats.get("paired", False)),
     }
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
@@ -213,7 +224,7 @@ def run_b200(args):
                 res["cpu_baseline"] = cpu_baseline(wl)
             except Exception as e:                      # the baseline must never lose the measured line
                 res["cpu_baseline"] = {"value": None, "unit": "s", "cores": 1, "kind": "port", "sample": "failed: %r" % (e,)}
-        print(json.dumps(res))
+        _emit(res)
     if world > 1:
         dist.destroy_process_group()
 
@@ -267,14 +278,31 @@ def run_reference(args):
            "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": round(v * 1e3, 1), "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic",
-           "config": {"workload": desc, "n_points": n, "n_eigenpairs": k},
+           "config": {"workload": desc, "n_points": n, "ambient_dim": 3, "n_eigenpairs": k, "n_neighbors": 10,
+                      "parallelism": "host CPU, 1 core (reference path)"},
            "cpu_baseline": dict(last, value=round(v, 1)),
            "e2e": {"value": round(v, 1), "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(res))
+    _emit(res)
+
+
+_REAL_STDOUT = None
+
+
+def _emit(res):
+    """The ONE JSON line of the contract, on the process's real stdout."""
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(res) + "\n")
+    out.flush()
 
 
 def main():
+    # stdout carries exactly one JSON line (rank 0): library banners (e.g. "NCCL version ...") and any stray prints
+    # of this process go to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2)

@@ -176,15 +176,15 @@ def run_b200(args):
     share = np.mean([(o[0].stats["eig_Lc"]["t_filter"] + o[0].stats["eig_L"]["t_filter"]) for o in outs]) / (ms / 1e3 / args.steps)
     traffic = None
     tp = os.path.join(ROOT, "profiles", "spmm_traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and not sharded:      # the capture is of the single-GPU launch
         try:
             traffic = json.load(open(tp)).get(wl)
             if isinstance(traffic, dict):
-                traffic = traffic.get(st.get("spmm_kernel", "gather"))
+                traffic = traffic.get(str(st.get("spmm_kernel", "gather")).split(" ")[0])
         except Exception:
             traffic = None
     kname = ("bsr_spmm_mma_native_kernel (FP64 mma.sync row-group SpMM, node-contiguous panels; fused Chebyshev step, d=%d, %d columns)"
-             if st.get("spmm_kernel") == "mma_native" else "bsr_spmm_v2_kernel (fused Chebyshev step, d=%d, %d columns)") % (A.d, panel)
+             if str(st.get("spmm_kernel")).startswith("mma_native") else "bsr_spmm_v2_kernel (fused Chebyshev step, d=%d, %d columns)") % (A.d, panel)
     roofline = {"bound": "hbm", "kernel": kname,
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "traffic": traffic, "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback",

@@ -18,6 +18,26 @@ import torch
 
 from ._cabi import get_handle, I64, U64
 
+_HOST_THREADS_SET = [False]
+
+
+def _host_lapack_threads():
+    """torchrun exports OMP_NUM_THREADS=1, which makes the small projected eigenproblems (LAPACK, host) single-threaded
+    on every rank; give each rank its share of the host cores instead.  No effect outside torchrun."""
+    if _HOST_THREADS_SET[0]:
+        return
+    _HOST_THREADS_SET[0] = True
+    import os
+    lw = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
+    if lw <= 1 or os.environ.get("OMP_NUM_THREADS", "") != "1" or os.environ.get("RVGP_HOST_THREADS", "") == "0":
+        return
+    try:
+        from threadpoolctl import threadpool_limits
+        n = int(os.environ.get("RVGP_HOST_THREADS", "0")) or max(1, min(16, (os.cpu_count() or 1) // lw))
+        threadpool_limits(limits=n, user_api="blas")
+    except Exception:
+        pass
+
 
 class BsrMatrix:
     """Device block-CSR matrix with d x d FP64 blocks (vals None => unit-weight graph Laplacian pattern)."""
@@ -363,6 +383,7 @@ def smallest_eigenpairs(A, k, upper_bound, lower_bound=0.0, tol=1e-12, nex=None,
     tol: residual tolerance relative to upper_bound, ||A x - theta x|| <= tol * upper_bound.
     Returns (evals (k,) float64 cuda, evecs (N, k) float64 cuda, unit-norm columns, ascending).
     """
+    _host_lapack_threads()
     dev = A.indptr.device
     h = get_handle(dev.index)
     N = A.nrows                       # LOCAL rows (== global rows on a single GPU)
@@ -628,6 +649,7 @@ def smallest_eigenpairs_paired(A, k, upper_bound, lower_bound=0.0, tol=1e-12, ne
     """Smallest k eigenpairs of a d = 2 block matrix ``A`` that commutes with J (all blocks scaled rotations), through its
     complex-Hermitian form.  Same contract as ``smallest_eigenpairs``: returns (evals (k,), evecs (N, k)) with unit-norm
     columns, ascending; columns 2j and 2j+1 are (v_j, J v_j) of the j-th complex eigenpair."""
+    _host_lapack_threads()
     dev = A.indptr.device
     h = get_handle(dev.index)
     assert A.d == 2

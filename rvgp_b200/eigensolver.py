@@ -18,25 +18,28 @@ import torch
 
 from ._cabi import get_handle, I64, U64
 
-_HOST_THREADS_SET = [False]
+_TPC = [None, 0]
 
 
-def _host_lapack_threads():
-    """torchrun exports OMP_NUM_THREADS=1, which makes the small projected eigenproblems (LAPACK, host) single-threaded
-    on every rank; give each rank its share of the host cores instead.  No effect outside torchrun."""
-    if _HOST_THREADS_SET[0]:
-        return
-    _HOST_THREADS_SET[0] = True
+def _lapack_ctx():
+    """Context for the host LAPACK sections (the m x m projected problems): a FEW BLAS threads.  Measured on the B200 box
+    (16 host cores, tools/host_lapack_probe.py, profiles/r01d_host_lapack.txt): one outer iteration's Cholesky + triangular
+    inverse + projection + eigh of a 640 x 640 problem takes 205 ms with OpenBLAS's default 16 threads, 51 ms with 4 and
+    86 ms with 1 (torchrun's OMP_NUM_THREADS=1).  Threads per rank: host cores / (4 * ranks on the node), clamped to [1, 4];
+    RVGP_HOST_THREADS overrides."""
+    import contextlib
     import os
-    lw = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
-    if lw <= 1 or os.environ.get("OMP_NUM_THREADS", "") != "1" or os.environ.get("RVGP_HOST_THREADS", "") == "0":
-        return
-    try:
-        from threadpoolctl import threadpool_limits
-        n = int(os.environ.get("RVGP_HOST_THREADS", "0")) or max(1, min(16, (os.cpu_count() or 1) // lw))
-        threadpool_limits(limits=n, user_api="blas")
-    except Exception:
-        pass
+    if _TPC[0] is None:
+        try:
+            from threadpoolctl import ThreadpoolController
+            lw = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
+            n = int(os.environ.get("RVGP_HOST_THREADS", "0") or 0) or max(1, min(4, (os.cpu_count() or 1) // (4 * max(1, lw))))
+            _TPC[0], _TPC[1] = ThreadpoolController(), n
+        except Exception:
+            _TPC[0] = False
+    if not _TPC[0]:
+        return contextlib.nullcontext()
+    return _TPC[0].limit(limits=_TPC[1], user_api="blas")
 
 
 class BsrMatrix:
@@ -383,7 +386,6 @@ def smallest_eigenpairs(A, k, upper_bound, lower_bound=0.0, tol=1e-12, nex=None,
     tol: residual tolerance relative to upper_bound, ||A x - theta x|| <= tol * upper_bound.
     Returns (evals (k,) float64 cuda, evecs (N, k) float64 cuda, unit-norm columns, ascending).
     """
-    _host_lapack_threads()
     dev = A.indptr.device
     h = get_handle(dev.index)
     N = A.nrows                       # LOCAL rows (== global rows on a single GPU)
@@ -472,8 +474,9 @@ def smallest_eigenpairs(A, k, upper_bound, lower_bound=0.0, tol=1e-12, nex=None,
             dense.gram(V, V, Gd, sym=True)
             G = dense.sym_to_host(Gd)
             t0 = time.perf_counter()
-            R, shifted = _chol_upper_shifted(G)
-            Rinv = _tri_inv_upper(R)
+            with _lapack_ctx():
+                R, shifted = _chol_upper_shifted(G)
+                Rinv = _tri_inv_upper(R)
             st["t_host"] += time.perf_counter() - t0
             Cd.copy_(torch.from_numpy(np.ascontiguousarray(Rinv)))
             dense.apply(V, Cd, W)                          # W = V R^-1   (nearly orthonormal)
@@ -489,12 +492,13 @@ def smallest_eigenpairs(A, k, upper_bound, lower_bound=0.0, tol=1e-12, nex=None,
         G = dense.sym_to_host(Gd)
         Hm = dense.sym_to_host(Hd)
         t0 = time.perf_counter()
-        R2 = np.linalg.cholesky(G).T
-        R2inv = _tri_inv_upper(R2)
-        Hm = R2inv.T @ Hm @ R2inv
-        Hm = 0.5 * (Hm + Hm.T)
-        theta, Y = np.linalg.eigh(Hm)
-        Cm = R2inv @ Y
+        with _lapack_ctx():
+            R2 = np.linalg.cholesky(G).T
+            R2inv = _tri_inv_upper(R2)
+            Hm = R2inv.T @ Hm @ R2inv
+            Hm = 0.5 * (Hm + Hm.T)
+            theta, Y = np.linalg.eigh(Hm)
+            Cm = R2inv @ Y
         st["t_host"] += time.perf_counter() - t0
         Cd.copy_(torch.from_numpy(np.ascontiguousarray(Cm)))
         theta_d.copy_(torch.from_numpy(theta))
@@ -649,7 +653,6 @@ def smallest_eigenpairs_paired(A, k, upper_bound, lower_bound=0.0, tol=1e-12, ne
     """Smallest k eigenpairs of a d = 2 block matrix ``A`` that commutes with J (all blocks scaled rotations), through its
     complex-Hermitian form.  Same contract as ``smallest_eigenpairs``: returns (evals (k,), evecs (N, k)) with unit-norm
     columns, ascending; columns 2j and 2j+1 are (v_j, J v_j) of the j-th complex eigenpair."""
-    _host_lapack_threads()
     dev = A.indptr.device
     h = get_handle(dev.index)
     assert A.d == 2
@@ -755,8 +758,9 @@ def smallest_eigenpairs_paired(A, k, upper_bound, lower_bound=0.0, tol=1e-12, ne
             rot90(V, JV)
             G = gram_c(V, JV, V, Gr, Gi)
             t0 = time.perf_counter()
-            R, shifted = _chol_upper_shifted_c(G)
-            Rinv = _tri_inv_upper(R)
+            with _lapack_ctx():
+                R, shifted = _chol_upper_shifted_c(G)
+                Rinv = _tri_inv_upper(R)
             st["t_host"] += time.perf_counter() - t0
             apply_c(V, JV, Rinv, W)
             V, W = W, V
@@ -769,12 +773,13 @@ def smallest_eigenpairs_paired(A, k, upper_bound, lower_bound=0.0, tol=1e-12, ne
         G = gram_c(V, JV, V, Gr, Gi)
         Hm = gram_c(V, JV, W, Hr, Hi)                      # V^H A V
         t0 = time.perf_counter()
-        R2 = np.linalg.cholesky(G).conj().T
-        R2inv = _tri_inv_upper(R2)
-        Hm = R2inv.conj().T @ Hm @ R2inv
-        Hm = 0.5 * (Hm + Hm.conj().T)
-        theta, Y = np.linalg.eigh(Hm)
-        Cm = R2inv @ Y
+        with _lapack_ctx():
+            R2 = np.linalg.cholesky(G).conj().T
+            R2inv = _tri_inv_upper(R2)
+            Hm = R2inv.conj().T @ Hm @ R2inv
+            Hm = 0.5 * (Hm + Hm.conj().T)
+            theta, Y = np.linalg.eigh(Hm)
+            Cm = R2inv @ Y
         st["t_host"] += time.perf_counter() - t0
         theta_d.copy_(torch.from_numpy(np.ascontiguousarray(theta)))
         apply_c(V, JV, Cm, W)                              # Ritz vectors

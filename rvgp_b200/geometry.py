@@ -307,33 +307,58 @@ def manifold_dimension(Sigma, frac_explained=0.9):
 
 
 def _csr_host(G):
-    return G.indptr.cpu().numpy(), G.indices.cpu().numpy()
+    """Host (indptr, indices, n) of the symmetric pattern with self loops: from a ManifoldGraph (device -> host copy) or
+    straight from a networkx graph (the reference's argument type; no device involved)."""
+    if isinstance(G, ManifoldGraph):
+        return G.indptr.cpu().numpy(), G.indices.cpu().numpy(), G.n
+    import networkx as nx
+    from scipy import sparse
+    M = sparse.csr_matrix(nx.adjacency_matrix(G, weight="weight"))
+    M = M.maximum(M.T).tocsr()
+    M.sort_indices()
+    return M.indptr.astype(np.int64), M.indices.astype(np.int64), M.shape[0]
 
 
 def compute_laplacian(G, normalization=False):
-    """Graph Laplacian D - A as scipy CSR f64 (geometry.py:55-63).  Host materialisation of the device
-    pattern: diagonal = number of non-self neighbours, off-diagonal = -1."""
-    if normalization:
-        raise NotImplementedError("normalized Laplacian is not reached from the hot path (SURVEY.md 2.1)")
+    """Graph Laplacian as scipy CSR f64 (geometry.py:55-63).  Host materialisation of the unit-weight pattern:
+    D - A has diagonal = number of non-self neighbours (the self loop cancels) and off-diagonal = -1;
+    ``normalization=True`` is networkx's ``normalized_laplacian_matrix``: D^-1/2 (D - A) D^-1/2 with D = row sums of A
+    INCLUDING the self loop."""
     from scipy import sparse
-    G = ManifoldGraph.from_any(G)
-    ip, ix = _csr_host(G)
-    rows = np.repeat(np.arange(G.n), np.diff(ip))
+    ip, ix, n = _csr_host(G)
+    rows = np.repeat(np.arange(n), np.diff(ip))
     deg = (np.diff(ip) - 1).astype(np.float64)
     data = np.where(rows == ix, deg[rows], -1.0)
-    return sparse.csr_matrix((data, ix.copy(), ip.copy()), shape=(G.n, G.n))
+    if normalization:
+        has_loop = np.zeros(n, dtype=bool)
+        has_loop[rows[rows == ix]] = True
+        dsum = np.diff(ip).astype(np.float64)                  # row sums of A (every stored entry has weight 1)
+        deg = dsum - has_loop                                  # diagonal of D - A
+        data = np.where(rows == ix, deg[rows], -1.0)
+        with np.errstate(divide="ignore"):
+            dh = 1.0 / np.sqrt(dsum)
+        dh[np.isinf(dh)] = 0.0
+        data = data * dh[rows] * dh[ix]
+    return sparse.csr_matrix((data, ix.copy(), ip.copy()), shape=(n, n))
 
 
 def compute_connection_laplacian(G, R, normalization=None):
-    """Connection Laplacian as scipy BSR (geometry.py:14-52): kron(L, 1_{dxd}) .* R."""
-    if normalization is not None:
-        raise NotImplementedError("normalization='rw' is not reached from the hot path (SURVEY.md 2.1)")
+    """Connection Laplacian as scipy sparse (geometry.py:14-52): kron(L, 1_{dxd}) .* R; ``normalization='rw'`` multiplies
+    row block i by 1 / deg_i with networkx's degree (a self loop counts twice, geometry.py:45-50)."""
     from scipy import sparse
-    G = ManifoldGraph.from_any(G)
-    n = G.n
+    ip, ix, n = _csr_host(G)
     dim = R.shape[0] // n
     L = compute_laplacian(G)
     Lc = sparse.kron(L, np.ones([dim, dim])).multiply(R)
+    if normalization == "rw":
+        rows = np.repeat(np.arange(n), np.diff(ip))
+        has_loop = np.zeros(n, dtype=bool)
+        has_loop[rows[rows == ix]] = True
+        deg = (np.diff(ip) + has_loop).astype(np.float64)      # nx degree: neighbours + 2 for the self loop
+        with np.errstate(divide="ignore"):
+            deg_inv = 1.0 / deg
+        deg_inv[np.isinf(deg_inv)] = 0
+        return sparse.diags(deg_inv.repeat(dim), 0, format="csr") @ Lc
     return sparse.bsr_matrix(Lc, blocksize=(dim, dim))
 
 

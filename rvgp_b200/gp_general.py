@@ -41,7 +41,8 @@ def _colsq_sum(h, A):
     return out
 
 
-def _split_for(K, tiles_elems):
+def _split_for(K):
+    """Deterministic split-K factor for products with a long contraction (K) and a small output."""
     return max(1, min(64, K // 2048)) if K >= 4096 else 1
 
 
@@ -112,7 +113,7 @@ class DenseGPR:
             Kmn = self.kernel._gram(self.X, Xc)              # (M, nc)
             ch.solve(Kmn, 0)                                 # A = L^-1 Kmn
             var[r0:r1] = self.kernel._diag(Xc) - _colsq_sum(h, Kmn)
-            split = _split_for(M, nc * R)
+            split = _split_for(M)
             ws = torch.empty(split * nc * R, dtype=torch.float64, device=self.dev) if split > 1 else None
             _dgemm(h, nc, R, M, Kmn, Kmn.stride(0), 0, alpha, alpha.stride(0), 0, mean[r0:r1], R, split_k=split, ws=ws)
         return mean, var.reshape(-1, 1).expand(Ns, R).contiguous()
@@ -145,7 +146,7 @@ class DeviceSGPR:
         Ap = self.kernel._gram(Z, self.X)                    # (Mu, N)
         chL.solve(Ap, 0)
         B = torch.empty((Mu, Mu), dtype=torch.float64, device=self.dev)
-        split = _split_for(N, Mu * Mu)
+        split = _split_for(N)
         ws = torch.empty(split * Mu * Mu, dtype=torch.float64, device=self.dev) if split > 1 else None
         _dgemm(h, Mu, Mu, N, Ap, Ap.stride(0), 1, Ap, Ap.stride(0), 1, B, B.stride(0), alpha=1.0 / noise, split_k=split, ws=ws)
         h.call("rvgp_add_diag_f64", B, I64(B.stride(0)), int(Mu), 1.0)

@@ -196,7 +196,8 @@ class RBF:
 
     def _adjoint(self, XA, XB, Gbar, want_dX=False):
         """Reverse mode of K(XA, XB) for the adjoint Gbar: {variance, lengthscales} gradients and dF/dXA.
-        Gbar is overwritten with H = Gbar o K when dF/dXA is wanted."""
+        The inner products are recomputed (one dgemm) instead of being kept from the forward pass; H = Gbar o K overwrites
+        that scratch, Gbar is left untouched."""
         h = get_handle(XA.device.index)
         A, B, k = XA.shape[0], XB.shape[0], XA.shape[1]
         dev = XA.device

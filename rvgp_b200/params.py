@@ -31,7 +31,7 @@ class positive:
         return y + np.log(-np.expm1(-y))
 
     def dforward(self, u):
-        return 1.0 / (1.0 + np.exp(-u))
+        return float(np.exp(-np.logaddexp(0.0, -u)))        # sigmoid(u) without overflow for large |u|
 
 
 class Parameter:

@@ -17,3 +17,22 @@ p, l = furthest_point_sampling(gd["X"], spacing=0.2); print("fps", len(p))
 from rvgp_b200.gp import DeviceGPR
 X = torch.randn((300, 20), dtype=torch.float64, device="cuda"); Y = torch.randn((300, 1), dtype=torch.float64, device="cuda")
 print(DeviceGPR(X, Y, solver="dense").lml_and_grads(np.ones(20), 0.5)[0])
+if "--new" in sys.argv or "--all" in sys.argv:
+    # kernels added late in round 1: K17 RBF Gram / adjoint, K18 SGPR + feature-space FPS (warp path, D > 64), K19 div/curl
+    # features, K20 orientation + paired eigensolver (sphere: orientable -> paired mode)
+    from rvgp_b200 import params as P
+    P.set_default_positive_minimum(0.0)
+    gs = load_golden("sphere_n2000_k50")
+    d = RVGP.create_data_object(gs["X"][:900], n_eigenpairs=20, verbose=False)
+    print("paired", d.stats["paired"], "converged", d.stats["eig_Lc"]["converged"])
+    d.random_vector_field(seed=1); d.smooth_vector_field(t=10)
+    tr = np.arange(0, d.n, 2)
+    for kern, nind in (("rbf", None), (None, 12), ("rbf", 9)):
+        gp = RVGP.fit(d, train_ind=tr, kernel=kern, n_inducing_points=nind, epochs=3)
+        print(kern, nind, type(gp).__name__, gp.l2_error)
+    x = np.random.default_rng(0).normal(size=(300, 130))
+    print("fps D=130", furthest_point_sampling(x, N=10)[0][:5])
+    from rvgp_b200.eeg_utils import compute_vectorfield_features
+    ge = load_golden("eeg_features")
+    dv, cl = compute_vectorfield_features(ge["positions"], ge["vectors"], k=5)
+    print("features", float(abs(dv - ge["div_k5"]).max()))

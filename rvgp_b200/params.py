@@ -31,7 +31,9 @@ class positive:
         return y + np.log(-np.expm1(-y))
 
     def dforward(self, u):
-        return float(np.exp(-np.logaddexp(0.0, -u)))        # sigmoid(u) without overflow for large |u|
+        if u < -700.0:                                   # exp(-u) would overflow; sigmoid underflows to 0 anyway
+            return 0.0
+        return 1.0 / (1.0 + np.exp(-u))
 
 
 class Parameter:

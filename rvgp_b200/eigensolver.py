@@ -402,8 +402,12 @@ def smallest_eigenpairs(A, k, upper_bound, lower_bound=0.0, tol=1e-12, nex=None,
     m = min(Nglob, k + nex)
     if panel is None:
         panel = 64 if m >= 128 else 32
-        if getattr(A, "vals", 1) is None and m >= 512 and comm is None:
-            panel = 128        # scalar pattern-mode Laplacian: 0.57 vs 0.52 of HBM peak with 128-column panels (measured)
+        import os
+        if getattr(A, "vals", 1) is None and m >= 512 and (comm is None or os.environ.get("RVGP_SHARDED_L_PANEL") == "128"):
+            # scalar pattern-mode Laplacian: 0.57 vs 0.52 of HBM peak with 128-column panels (measured on one GPU).  Row-sharded
+            # runs keep 64 until measured: RVGP_SHARDED_L_PANEL=128 opts in (8 GPUs: 9 791 steps of 0.09 ms are latency-bound,
+            # half as many 128-column steps should cost less; DESIGN.md "next")
+            panel = 128
     if m < Nglob:
         m = min(Nglob, ((m + panel - 1) // panel) * panel)
     hi = float(upper_bound)

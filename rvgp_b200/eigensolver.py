@@ -417,6 +417,8 @@ def smallest_eigenpairs(A, k, upper_bound, lower_bound=0.0, tol=1e-12, nex=None,
         hi = min(hi, 1.01 * lanczos_upper_bound(A, comm=comm, h=h))
     lo_spec = float(lower_bound)
     tol_abs = tol * float(upper_bound)
+    import os as _os
+    cond_max = float(_os.environ.get("RVGP_EIG_COND_MAX", cond_max))     # policy knob (profiles/r01d_eig_policy_emulation.txt)
     st = stats if stats is not None else {}
     st.update(dict(N=N, k=k, m=m, panel=panel, spmm_launches=0, filter_launches=0, filter_col_degrees=0, outer=0,
                    t_filter=0.0, t_dense=0.0, t_host=0.0, spmm_bytes_fused=int(A.spmm_bytes(panel, fused=True)),
@@ -683,6 +685,8 @@ def smallest_eigenpairs_paired(A, k, upper_bound, lower_bound=0.0, tol=1e-12, ne
         hi = min(hi, 1.01 * lanczos_upper_bound(A, comm=comm, h=h))
     lo_spec = float(lower_bound)
     tol_abs = tol * float(upper_bound)
+    import os as _os
+    cond_max = float(_os.environ.get("RVGP_EIG_COND_MAX", cond_max))     # policy knob (profiles/r01d_eig_policy_emulation.txt)
     st = stats if stats is not None else {}
     st.update(dict(N=N, k=k, m=mc, paired=True, panel=panel, spmm_launches=0, filter_launches=0, filter_col_degrees=0,
                    outer=0, t_filter=0.0, t_dense=0.0, t_host=0.0, spmm_bytes_fused=int(A.spmm_bytes(panel, fused=True)),

@@ -71,9 +71,14 @@ if __name__ == "__main__":
     hi_g = 2.0 * (np.diff(ip).max() - 1)
     hi = 1.01 * float(sp.linalg.eigsh(A, 1, which="LA", return_eigenvectors=False)[0])
     base = None
-    for name, kw in (("default", {}), ("deg0=40", dict(deg0=40)), ("deg0=80", dict(deg0=80)), ("cond 1e8", dict(cond_max=1e8)),
-                     ("cond 1e10", dict(cond_max=1e10)), ("decade 2", dict(decade=2.0)), ("margin 1.0", dict(margin=1.0)),
-                     ("nex 2x", dict(nex=max(32, int(0.4 * k)))), ("deg0=40 cond 1e8 decade 2", dict(deg0=40, cond_max=1e8, decade=2.0))):
+    variants = (("default", {}), ("deg0=40", dict(deg0=40)), ("deg0=80", dict(deg0=80)), ("cond 1e8", dict(cond_max=1e8)),
+                ("cond 1e10", dict(cond_max=1e10)), ("decade 2", dict(decade=2.0)), ("margin 1.0", dict(margin=1.0)),
+                ("nex 0.4k", dict(nex=max(32, int(0.4 * k)))), ("nex 0.1k", dict(nex=max(16, int(0.1 * k)))),
+                ("deg0=40 cond 1e8 decade 2", dict(deg0=40, cond_max=1e8, decade=2.0)))
+    only = os.environ.get("EMU_VARIANTS")
+    if only:
+        variants = tuple(v for v in variants if v[0] in only.split(";"))
+    for name, kw in variants:
         t0 = time.perf_counter()
         r = solve(A, k, hi_g, hi=hi, **kw)
         if base is None:

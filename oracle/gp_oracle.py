@@ -16,6 +16,8 @@ reference's own call sites:
   gpflow/likelihoods       Gaussian(variance=1.0, lower bound 1e-6)
   gpflow/optimizers/scipy.py     scipy.optimize.minimize(jac=True, method="l-bfgs-b")
 
+Independent third-party cross-pin: tests/test_gp_oracle_vs_sklearn.py compares the GPR equations below with scikit-learn's
+GaussianProcessRegressor (available here) to 1e-9 or better -- not GPflow, hence still 'unpinned'.
 Cross-checks that stand in for pins (tests/test_gp_oracle.py): analytic gradients vs central differences,
 K_diag == diag(K), dense Cholesky GPR == rank-k (Woodbury) GPR, the survey's independent probe value of the
 initial LML on config C1 (-2512.1283414532).

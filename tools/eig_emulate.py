@@ -11,29 +11,35 @@ from tests.workloads import make_cloud
 from oracle import rvgp_oracle as O
 
 
-def cheb(A, V, deg, lo, cut, hi):
+def cheb(A, V, deg, lo, cut, hi, f32=False):
+    if f32:                                   # FP32 panels AND FP32 matrix values: what a half-width filter kernel would do
+        A = A.astype(np.float32); V = V.astype(np.float32)
     e = 0.5 * (hi - cut); c = 0.5 * (hi + cut); s1 = e / (lo - c); tau = 2 / s1; sig = s1
     Y = (A @ V - c * V) * (s1 / e); X = V
     for _ in range(2, deg + 1):
         sn = 1 / (tau - sig)
         Yn = (A @ Y - c * Y) * (2 * sn / e) - sig * sn * X
         X, Y = Y, Yn; sig = sn
-    return Y
+    return Y.astype(np.float64)
 
 
-def solve(A, k, hi_g, nex=None, panel=64, deg0=20, cond_max=1e6, margin=1.05, decade=10.0, tol=1e-12, hi=None, seed=0, V0=None):
+def solve(A, k, hi_g, nex=None, panel=64, deg0=20, cond_max=1e6, margin=1.05, decade=10.0, tol=1e-12, hi=None, seed=0, V0=None,
+          f32_until=0.0):
+    """f32_until: filter in FP32 while the largest wanted residual is above f32_until * hi_g (0 = always FP64)."""
     N = A.shape[0]
     nex = max(16, int(math.ceil(0.2 * k))) if nex is None else nex
     m = ((k + nex + panel - 1) // panel) * panel
     hi = hi or hi_g
     tol_abs = tol * hi_g
     V = np.random.default_rng(seed).uniform(-1, 1, (N, m)) if V0 is None else V0.copy()
-    deg = np.full(m, deg0); a_cut = 0.3 * hi; coldeg = 0; passes = 0
+    deg = np.full(m, deg0); a_cut = 0.3 * hi; coldeg = 0; passes = 0; f32deg = 0; worst = np.inf
     for it in range(80):
         for p0 in range(0, m, panel):
             dg = int(deg[p0:p0 + panel].max())
             if dg > 0:
-                V[:, p0:p0 + panel] = cheb(A, V[:, p0:p0 + panel], dg, 0.0, a_cut, hi); coldeg += dg * panel
+                use32 = worst > f32_until * hi_g and f32_until > 0
+                V[:, p0:p0 + panel] = cheb(A, V[:, p0:p0 + panel], dg, 0.0, a_cut, hi, f32=use32); coldeg += dg * panel
+                f32deg += dg * panel if use32 else 0
         for _ in range(4):
             V /= np.sqrt((V * V).sum(0)); R, sh = _chol_upper_shifted(V.T @ V); V = V @ _tri_inv_upper(R); passes += 1
             if not sh: break
@@ -43,7 +49,7 @@ def solve(A, k, hi_g, nex=None, panel=64, deg0=20, cond_max=1e6, margin=1.05, de
         Hm = R2inv.T @ H @ R2inv; th, Y = np.linalg.eigh(0.5 * (Hm + Hm.T))
         V = V @ (R2inv @ Y)
         res = np.sqrt((((A @ V) - V * th) ** 2).sum(0))
-        nconv = int((res[:k] <= tol_abs).sum())
+        nconv = int((res[:k] <= tol_abs).sum()); worst = float(res[:k].max())
         a_cut = float(th[-1])
         if nconv == k:
             break
@@ -57,7 +63,7 @@ def solve(A, k, hi_g, nex=None, panel=64, deg0=20, cond_max=1e6, margin=1.05, de
         d = np.ceil(np.minimum(need * margin + 1.0, cap)); d[res <= tol_abs] = 0
         d[k:] = np.minimum(d[k:], d[:k].max())
         deg = np.minimum(d, 6000).astype(np.int64)
-    return dict(outer=it + 1, coldeg=coldeg, per_col=coldeg / m, m=m, passes=passes, maxres=float(res[:k].max()), evals=th[:k])
+    return dict(f32deg=f32deg, outer=it + 1, coldeg=coldeg, per_col=coldeg / m, m=m, passes=passes, maxres=float(res[:k].max()), evals=th[:k])
 
 
 if __name__ == "__main__":
@@ -74,7 +80,8 @@ if __name__ == "__main__":
     variants = (("default", {}), ("deg0=40", dict(deg0=40)), ("deg0=80", dict(deg0=80)), ("cond 1e8", dict(cond_max=1e8)),
                 ("cond 1e10", dict(cond_max=1e10)), ("decade 2", dict(decade=2.0)), ("margin 1.0", dict(margin=1.0)),
                 ("nex 0.4k", dict(nex=max(32, int(0.4 * k)))), ("nex 0.1k", dict(nex=max(16, int(0.1 * k)))),
-                ("deg0=40 cond 1e8 decade 2", dict(deg0=40, cond_max=1e8, decade=2.0)))
+                ("deg0=40 cond 1e8 decade 2", dict(deg0=40, cond_max=1e8, decade=2.0)),
+                ("fp32 until 1e-5", dict(f32_until=1e-5)), ("fp32 until 1e-6", dict(f32_until=1e-6)), ("fp32 until 1e-7", dict(f32_until=1e-7)))
     only = os.environ.get("EMU_VARIANTS")
     if only:
         variants = tuple(v for v in variants if v[0] in only.split(";"))
@@ -83,6 +90,6 @@ if __name__ == "__main__":
         r = solve(A, k, hi_g, hi=hi, **kw)
         if base is None:
             base = r
-        print("%-28s outer %2d  cholqr %2d  m %4d  col-degrees %9d (%.2fx)  per column %6.0f  maxres %.1e  evals dev %.1e  %.0f s" %
-              (name, r["outer"], r["passes"], r["m"], r["coldeg"], r["coldeg"] / base["coldeg"], r["per_col"], r["maxres"],
+        print("%-28s outer %2d  cholqr %2d  m %4d  col-degrees %9d (%.2fx, %2.0f%% in fp32)  per column %6.0f  maxres %.1e  evals dev %.1e  %.0f s" %
+              (name, r["outer"], r["passes"], r["m"], r["coldeg"], r["coldeg"] / base["coldeg"], 100.0 * r["f32deg"] / r["coldeg"], r["per_col"], r["maxres"],
                np.abs(r["evals"] - base["evals"]).max(), time.perf_counter() - t0), flush=True)

@@ -20,7 +20,7 @@ def tangent_frames(X, G, d, K):
         raise ValueError("Geodesic neighborhood size must be larger or equal to the embedding dimension")
     if D < d:
         raise ValueError("Embedding dimension must be less or equal to the ambient dimension of input data")
-    g = _geo.ManifoldGraph.from_any(G)
+    g = _geo.ManifoldGraph.from_any(G, unit_weights_only=True)
     Xd = _geo.to_device_f64(X, g.indptr.device)
     seq, _ = _geo.geodesic_neighbourhoods_device(g.indptr, g.indices, int(K))
     T, S = _geo.tangent_frames_device(Xd, seq, int(d))

@@ -181,7 +181,10 @@ class data:
                 self.stats["spmm_mma"] = S_Lc.enable_mma() is not None
             counts = [int(bounds[r + 1] - bounds[r]) for r in range(world)]
             self.stats["halo"] = dict(n_loc=plan.n_loc, n_halo=plan.n_halo, send=sum(plan.send_counts))
-            evals_L, U_loc = smallest_eigenpairs(S_L, k_L, upper_bound=hi, tol=eig_tol, stats=st_L, comm=comm)
+            try:
+                evals_L, U_loc = smallest_eigenpairs(S_L, k_L, upper_bound=hi, tol=eig_tol, stats=st_L, comm=comm)
+            finally:
+                S_L.close()                   # frees the cudaMalloc / CUDA-IPC halo buffers and the peer mappings
             U_L_p = comm.allgather_rows(U_loc, counts)
             self.timings["eig_L"] = tick() - t0
             t0 = tick()
@@ -193,10 +196,13 @@ class data:
                 hh.call("rvgp_lift_guess", G, geo.I64(r1 - r0), int(D), int(dim_man), U, geo.I64(U.stride(0)),
                         int(U.shape[1]), V, geo.I64(V.stride(0)), int(ncols))
 
-            evals_Lc, U_loc = eig_Lc(S_Lc, k_Lc, upper_bound=hi, tol=eig_tol, stats=st_Lc, comm=comm,
-                                     init_fn=lc_guess_loc if warm_start else None)
+            try:
+                evals_Lc, U_loc = eig_Lc(S_Lc, k_Lc, upper_bound=hi, tol=eig_tol, stats=st_Lc, comm=comm,
+                                         init_fn=lc_guess_loc if warm_start else None)
+            finally:
+                S_Lc.close()
             U_Lc_p = comm.allgather_rows(U_loc, [c * dim_man for c in counts])
-            del U_loc
+            del U_loc, S_L, S_Lc, plan
             self.timings["eig_Lc"] = tick() - t0
         else:
             evals_L, U_L_p = smallest_eigenpairs(A_L, k_L, upper_bound=hi, tol=eig_tol, stats=st_L)
@@ -223,25 +229,37 @@ class data:
         t0 = tick()
         # un-permute; scale by sqrt(#rows) (geometry.py:75); lift T u to ambient coordinates (dataclass.py:57-59)
         evecs_L = geo.gather_rows_device(U_L_p.contiguous(), inv)
+        del U_L_p
         h = geo.get_handle(dev.index)
         kk = evecs_L.shape[1]
         sc = torch.full((kk,), float(np.sqrt(N_L)), dtype=torch.float64, device=dev)
         h.call("rvgp_colscale_f64", geo.I64(N_L), int(kk), evecs_L, geo.I64(evecs_L.stride(0)), sc)
         kc = U_Lc_p.shape[1]
         lifted_p = geo.frame_apply_device(gauges_p, U_Lc_p.contiguous().reshape(n, dim_man, kc), 1, scale=float(np.sqrt(N_Lc)))
+        del U_Lc_p
         evecs_Lc = geo.gather_rows_device(lifted_p.reshape(n * D, kc), inv, block=D)
         del lifted_p
         self.timings["lift"] = tick() - t0
 
-        # device-resident state used by smooth_vector_field / fit
+        # device-resident state used by smooth_vector_field / fit.  Only ONE copy of each eigenvector matrix is kept (C4:
+        # evecs_Lc 12 GB + evecs_L 4 GB); the unit-norm Morton-ordered local-coordinate forms that the smoothing deflation
+        # needs are re-derived from them on first use (_U_Lc_p / _U_L_p below).  The private references survive a user
+        # overwriting d.evecs_Lc / d.evecs_L (the reference's ablation scripts do), so smoothing always sees the true basis.
         self._graph = graph
         self._Xd = Xd
         self._perm = (order, inv)
         self._A_Lc_p, self._A_L_p = A_Lc, A_L
-        self._U_Lc_p, self._U_L_p = U_Lc_p, U_L_p           # unit-norm, permuted row order
+        self._eig_dev = {"L": evecs_L, "Lc": evecs_Lc}
+        self._U_cache = {}
         self._evals_Lc_d, self._evals_L_d = evals_Lc, evals_L
         self._gauges_p = gauges_p
         self._hi = hi
+        for name, st in (("L", st_L), ("Lc", st_Lc)):
+            if st and not st.get("converged", True):
+                # scipy's eigsh raises ArpackNoConvergence here (geometry.py:73); unconverged pairs would silently corrupt the
+                # GP kernel and the smoothing deflation, which assumes an exact invariant subspace
+                raise RuntimeError("eigensolver for %s did not converge: max residual %.3e > tolerance %.3e after %d outer "
+                                   "iterations" % (name, st["residual_max"], eig_tol * hi, st["outer"]))
 
         self.vertices = vertices
         self.n = n
@@ -274,6 +292,35 @@ class data:
             self._duals["vectors"] = _Dual(dev=value)
         else:
             self._duals["vectors"] = _Dual(host=np.asarray(value))
+
+    # unit-norm eigenvectors in the Morton order of the spectral stage (local coordinates for Lc), derived on first use
+    @property
+    def _U_L_p(self):
+        if "L" not in self._U_cache:
+            order, _ = self._perm
+            U = geo.gather_rows_device(self._eig_dev["L"], order)
+            h = geo.get_handle(self.device.index)
+            sc = torch.full((U.shape[1],), 1.0 / float(np.sqrt(self.n)), dtype=torch.float64, device=self.device)
+            h.call("rvgp_colscale_f64", geo.I64(U.shape[0]), int(U.shape[1]), U, geo.I64(U.stride(0)), sc)
+            self._U_cache["L"] = U
+        return self._U_cache["L"]
+
+    @property
+    def _U_Lc_p(self):
+        if "Lc" not in self._U_cache:
+            order, _ = self._perm
+            n, d = self.n, self.dim_man
+            Phi = self._eig_dev["Lc"]
+            D, kc = Phi.shape[0] // n, Phi.shape[1]
+            Pp = geo.gather_rows_device(Phi, order, block=D)
+            # T^T (T u) = u: the gauges have orthonormal columns, so the local coordinates come back to rounding
+            U = geo.frame_apply_device(self._gauges_p, Pp.reshape(n, D, kc), 0, scale=1.0 / float(np.sqrt(n * d)))
+            self._U_cache["Lc"] = U.reshape(n * d, kc)
+        return self._U_cache["Lc"]
+
+    def release_cache(self):
+        """Drop the derived Morton-ordered eigenvector copies (C4: 12 GB); they are rebuilt on demand."""
+        self._U_cache.clear()
 
     def device_array(self, name):
         """Device tensor of a dual attribute (uploads a user-assigned host value on first use)."""

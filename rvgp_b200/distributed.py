@@ -9,6 +9,8 @@ with all_reduce, after which every rank solves the identical small projected pro
 
 ``HaloPlan`` is pure index logic on torch tensors (CPU or CUDA) so it is covered by the world_size-2 gloo tests.
 """
+import weakref
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -179,33 +181,57 @@ class PeerHalo:
         world, rank, group = plan.world, plan.rank, plan.group
         row_bytes = d * self.ncols * 8
         ebytes = max(256, (plan.n_loc + plan.n_halo) * row_bytes)
+        sizes = [ebytes, ebytes, ebytes, 8 * max(world, 32)]          # three rotating block vectors + the flag array
         self._own, self._opened = [], []
+        # the raw allocations outlive neither this object nor the process: close() is the orderly (collective) release,
+        # the finaliser the last resort when the object is dropped without it
+        self._finalizer = weakref.finalize(self, _release_ipc, lib, h._h, self._opened, self._own)
 
-        def shared(nbytes):
-            ptr = ctypes.c_void_p()
-            hd = (ctypes.c_uint8 * 64)()
-            rc = lib.rvgp_ipc_alloc(h._h, ctypes.c_int64(nbytes), ctypes.byref(ptr), hd)
-            if rc != 0:
-                raise RuntimeError("rvgp_ipc_alloc: " + lib.rvgp_last_error(h._h).decode())
-            self._own.append(ptr.value)
-            gathered = [None] * world
-            dist.all_gather_object(gathered, bytes(hd), group=group)
-            ptrs = []
-            for q in range(world):
-                if q == rank:
-                    ptrs.append(ptr.value)
-                    continue
-                pp = ctypes.c_void_p()
-                hq = (ctypes.c_uint8 * 64).from_buffer_copy(gathered[q])
-                rc = lib.rvgp_ipc_open(h._h, hq, ctypes.byref(pp))
+        # Failure-atomic setup: every rank runs the SAME collectives whatever fails locally.
+        #   phase 1  local allocations only                     -> all_gather_object of (ok, handles)
+        #   phase 2  open the peers' handles (only if all ok)   -> all_reduce(MIN) of ok
+        # A failure on any rank makes every rank release what it holds and raise the same error.
+        err, handles = None, []
+        try:
+            for nbytes in sizes:
+                ptr = ctypes.c_void_p()
+                hd = (ctypes.c_uint8 * 64)()
+                rc = lib.rvgp_ipc_alloc(h._h, ctypes.c_int64(nbytes), ctypes.byref(ptr), hd)
                 if rc != 0:
-                    raise RuntimeError("rvgp_ipc_open: " + lib.rvgp_last_error(h._h).decode())
-                self._opened.append(pp.value)
-                ptrs.append(pp.value)
-            return ptrs
-
-        self.E_ptrs = [shared(ebytes) for _ in range(3)]              # [slot][rank] -> device address
-        self.flag_ptrs = shared(8 * max(world, 32))
+                    raise RuntimeError("rvgp_ipc_alloc: " + lib.rvgp_last_error(h._h).decode())
+                self._own.append(ptr.value)
+                handles.append(bytes(hd))
+        except Exception as e:
+            err = e
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (err is None, handles), group=group)
+        if not all(g[0] for g in gathered):
+            self._finalizer()
+            raise RuntimeError("peer halo setup failed on rank(s) %s%s" %
+                               ([q for q, g in enumerate(gathered) if not g[0]], "" if err is None else ": %s" % (err,)))
+        table = [[None] * world for _ in sizes]                      # [buffer][rank] -> device address
+        try:
+            for b_i in range(len(sizes)):
+                for q in range(world):
+                    if q == rank:
+                        table[b_i][q] = self._own[b_i]
+                        continue
+                    pp = ctypes.c_void_p()
+                    hq = (ctypes.c_uint8 * 64).from_buffer_copy(gathered[q][1][b_i])
+                    rc = lib.rvgp_ipc_open(h._h, hq, ctypes.byref(pp))
+                    if rc != 0:
+                        raise RuntimeError("rvgp_ipc_open: " + lib.rvgp_last_error(h._h).decode())
+                    self._opened.append(pp.value)
+                    table[b_i][q] = pp.value
+        except Exception as e:
+            err = e
+        ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) != 1:
+            self.close(collective=True)        # every rank is here: peers unmap before owners free
+            raise RuntimeError("peer halo setup failed (cudaIpcOpenMemHandle)%s" % ("" if err is None else ": %s" % (err,)))
+        self.E_ptrs = table[:3]                                       # [slot][rank] -> device address
+        self.flag_ptrs = table[3]
         nrows_ext = (plan.n_loc + plan.n_halo) * d
         self.E = [torch.as_tensor(_DevMem(self.E_ptrs[s][rank], ebytes), device=dev).view(torch.float64)[: nrows_ext * self.ncols]
                   .view(nrows_ext, self.ncols) for s in range(3)]
@@ -276,14 +302,30 @@ class PeerHalo:
         if int(self.err.item()) != 0:
             raise RuntimeError("peer halo exchange timed out waiting for a neighbour rank (rvgp_halo_ctx.err)")
 
-    def close(self):
+    def close(self, collective=True):
+        """Release the peer mappings and this rank's buffers.  ``collective=True`` (every rank calls it at the same point)
+        puts a barrier between the two so that no owner frees memory a peer still has mapped; ``collective=False`` is for
+        error paths where the other ranks may never arrive."""
+        if not self._finalizer.alive:
+            return
         lib, hh = self.h.lib, self.h._h
         import ctypes
+        torch.cuda.synchronize(self.err.device if hasattr(self, "err") else None)
         for p in self._opened:
             lib.rvgp_ipc_close(hh, ctypes.c_void_p(p))
-        for p in self._own:
-            lib.rvgp_ipc_free(hh, ctypes.c_void_p(p))
-        self._opened, self._own = [], []
+        del self._opened[:]
+        if collective and dist.is_initialized():
+            dist.barrier(group=self.op.plan.group)
+        self._finalizer()                      # frees what is left (own buffers), exactly once
+
+
+def _release_ipc(lib, hh, opened, own):
+    import ctypes
+    for p in opened:
+        lib.rvgp_ipc_close(hh, ctypes.c_void_p(p))
+    for p in own:
+        lib.rvgp_ipc_free(hh, ctypes.c_void_p(p))
+    del opened[:], own[:]
 
 
 class ShardedBsr:
@@ -306,6 +348,16 @@ class ShardedBsr:
         self.mma = None
 
     peer_halo = True                    # halo exchange by our own kernels over NVLink peer memory (csrc/halo.cu)
+
+    def close(self, collective=True):
+        """Release every PeerHalo of this operator (raw cudaMalloc / CUDA-IPC memory torch does not own) and the scratch
+        block vectors.  Collective by default: call it on every rank at the same point."""
+        for nc in sorted(self._peer):
+            ph = self._peer[nc]
+            if ph is not None:
+                ph.close(collective=collective)
+        self._peer.clear()
+        self._bufs.clear()
 
     @property
     def spmm_kernel_name(self):

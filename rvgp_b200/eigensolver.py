@@ -533,9 +533,24 @@ def smallest_eigenpairs(A, k, upper_bound, lower_bound=0.0, tol=1e-12, nex=None,
         st["spmm_kernel"] = A.spmm_kernel_name
     st["residual_max"] = float(res[:k].max())
     st["converged"] = bool((res[:k] <= tol_abs).all())
+    st["tol_abs"] = tol_abs
+    _warn_unconverged(st, max_outer)
     evals = theta_d[:k].clone()
     evecs = V[:, :k].contiguous()     # copy out so the (N x m) work buffers can be freed
     return evals, evecs
+
+
+class EigenConvergenceWarning(RuntimeWarning):
+    """The block eigensolver stopped at max_outer without meeting the residual tolerance (scipy's eigsh raises
+    ArpackNoConvergence in the same situation, geometry.py:73)."""
+
+
+def _warn_unconverged(st, max_outer):
+    if not st["converged"]:
+        import warnings
+        warnings.warn("eigensolver stopped after %d outer iterations with max residual %.3e > tolerance %.3e; the returned "
+                      "pairs are NOT converged" % (st.get("outer", max_outer), st["residual_max"], st["tol_abs"]),
+                      EigenConvergenceWarning, stacklevel=3)
 
 
 def lanczos_upper_bound(A, steps=24, seed=12345, comm=None, h=None):
@@ -815,6 +830,8 @@ def smallest_eigenpairs_paired(A, k, upper_bound, lower_bound=0.0, tol=1e-12, ne
         st["spmm_kernel"] = A.spmm_kernel_name
     st["residual_max"] = float(res[:kc].max())
     st["converged"] = bool((res[:kc] <= tol_abs).all())
+    st["tol_abs"] = tol_abs
+    _warn_unconverged(st, max_outer)
     # expand every complex pair (theta_j, v_j) to the two real eigenpairs (theta_j, v_j), (theta_j, J v_j)
     del W, B1, B2                                        # V keeps the buffer it points to
     Vk = V[:, :kc]

@@ -236,11 +236,13 @@ def frame_apply_device(gauges, x, mode, scale=1.0):
 # public API (reference names)
 # ---------------------------------------------------------------------------------------------------------
 class ManifoldGraph:
-    """Device CSR of the symmetrised kNN graph with self loops.  ``to_networkx()`` materialises the
-    reference's networkx object (geometry.py:112,120-121) on demand."""
+    """Device CSR of a symmetric graph (the symmetrised kNN graph with self loops on the hot path).  ``weights`` is None
+    for unit weights (the hot path: pattern only) or a device f64 tensor, one weight per stored entry (typ='affinity',
+    weighted networkx input).  ``to_networkx()`` materialises the reference's networkx object (geometry.py:112,120-121)
+    on demand."""
 
-    def __init__(self, indptr, indices, X=None, knn=None):
-        self.indptr, self.indices, self.X, self.knn = indptr, indices, X, knn
+    def __init__(self, indptr, indices, X=None, knn=None, weights=None):
+        self.indptr, self.indices, self.X, self.knn, self.weights = indptr, indices, X, knn, weights
         self.n = indptr.numel() - 1
         self._nx = None
 
@@ -258,7 +260,8 @@ class ManifoldGraph:
         from scipy import sparse
         ip = self.indptr.cpu().numpy()
         ix = self.indices.cpu().numpy()
-        return sparse.csr_matrix((np.ones(ix.size), ix, ip), shape=(self.n, self.n))
+        w = np.ones(ix.size) if self.weights is None else self.weights.cpu().numpy().reshape(-1)
+        return sparse.csr_matrix((w, ix, ip), shape=(self.n, self.n))
 
     def to_networkx(self):
         if self._nx is None:
@@ -271,18 +274,25 @@ class ManifoldGraph:
         return self._nx
 
     @staticmethod
-    def from_any(G, device=None):
-        """Accept a ManifoldGraph or a networkx graph (the reference's inner-FFI argument type)."""
-        if isinstance(G, ManifoldGraph):
-            return G
-        import networkx as nx
-        from scipy import sparse
-        M = sparse.csr_matrix(nx.adjacency_matrix(G, weight="weight"))
-        M = M.maximum(M.T).tocsr()
-        M.sort_indices()
-        dev = _dev(device)
-        return ManifoldGraph(torch.from_numpy(M.indptr.astype(np.int32)).to(dev),
-                             torch.from_numpy(M.indices.astype(np.int32)).to(dev))
+    def from_any(G, device=None, unit_weights_only=False):
+        """Accept a ManifoldGraph or a networkx graph (the reference's inner-FFI argument type): adjacency with weights,
+        symmetrised with the element-wise maximum like pyx:84-103.  ``unit_weights_only``: the caller's kernel walks the
+        pattern with unit edge lengths (the heap-Dijkstra emulation) -- anything else is refused, not silently changed."""
+        if not isinstance(G, ManifoldGraph):
+            import networkx as nx
+            from scipy import sparse
+            M = sparse.csr_matrix(nx.adjacency_matrix(G, weight="weight"), dtype=np.float64)
+            M = M.maximum(M.T).tocsr()
+            M.sort_indices()
+            dev = _dev(device)
+            unit = bool(np.all(M.data == 1.0))
+            G = ManifoldGraph(torch.from_numpy(M.indptr.astype(np.int32)).to(dev),
+                              torch.from_numpy(M.indices.astype(np.int32)).to(dev),
+                              weights=None if unit else torch.from_numpy(np.ascontiguousarray(M.data)).to(dev))
+        if unit_weights_only and G.weights is not None:
+            raise NotImplementedError("geodesic neighbourhoods on a graph with non-unit edge weights are not on the B200 "
+                                      "hot path (the reference pipeline only builds unit-weight kNN graphs, geometry.py:103-112)")
+        return G
 
 
 def manifold_graph(X, typ="knn", n_neighbors=5, device=None):
@@ -306,55 +316,63 @@ def manifold_dimension(Sigma, frac_explained=0.9):
     return int(dim_man)
 
 
-def _csr_host(G):
-    """Host (indptr, indices, n) of the symmetric pattern with self loops: from a ManifoldGraph (device -> host copy) or
-    straight from a networkx graph (the reference's argument type; no device involved)."""
-    if isinstance(G, ManifoldGraph):
-        return G.indptr.cpu().numpy(), G.indices.cpu().numpy(), G.n
-    import networkx as nx
+def _adjacency_host(G):
+    """Host scipy CSR adjacency WITH weights, the matrix networkx hands to its Laplacian builders
+    (``nx.to_scipy_sparse_array(G, weight='weight')``: a self loop appears once on the diagonal).  From a ManifoldGraph
+    (device -> host copy; unit weights unless the graph carries some) or straight from a networkx graph (the reference's
+    argument type; no device involved)."""
     from scipy import sparse
-    M = sparse.csr_matrix(nx.adjacency_matrix(G, weight="weight"))
-    M = M.maximum(M.T).tocsr()
-    M.sort_indices()
-    return M.indptr.astype(np.int64), M.indices.astype(np.int64), M.shape[0]
+    if isinstance(G, ManifoldGraph):
+        return G.scipy_adjacency()
+    import networkx as nx
+    A = sparse.csr_matrix(nx.to_scipy_sparse_array(G, weight="weight", format="csr"), dtype=np.float64)
+    A.sort_indices()
+    return A
 
 
 def compute_laplacian(G, normalization=False):
-    """Graph Laplacian as scipy CSR f64 (geometry.py:55-63).  Host materialisation of the unit-weight pattern:
-    D - A has diagonal = number of non-self neighbours (the self loop cancels) and off-diagonal = -1;
-    ``normalization=True`` is networkx's ``normalized_laplacian_matrix``: D^-1/2 (D - A) D^-1/2 with D = row sums of A
-    INCLUDING the self loop."""
+    """Graph Laplacian as scipy CSR f64 (geometry.py:55-63) = networkx's ``laplacian_matrix`` / ``normalized_laplacian_matrix``
+    restated on the host: L = diag(rowsum(A)) - A with an explicit diagonal, edge weights kept (so loop-free and weighted
+    graphs, e.g. typ='affinity', are handled like the pipeline's unit-weight kNN graph with self loops, where the self
+    loop cancels and the diagonal is the number of non-self neighbours); ``normalization=True``: D^-1/2 L D^-1/2 with
+    D = rowsum(A) INCLUDING the self loop, 1/sqrt(0) -> 0."""
     from scipy import sparse
-    ip, ix, n = _csr_host(G)
-    rows = np.repeat(np.arange(n), np.diff(ip))
-    deg = (np.diff(ip) - 1).astype(np.float64)
-    data = np.where(rows == ix, deg[rows], -1.0)
+    A = _adjacency_host(G)
+    n = A.shape[0]
+    dsum = np.asarray(A.sum(axis=1)).reshape(-1)
+    L = sparse.csr_matrix(sparse.diags(dsum, 0, shape=(n, n), format="csr") - A, dtype=np.float64)
     if normalization:
-        has_loop = np.zeros(n, dtype=bool)
-        has_loop[rows[rows == ix]] = True
-        dsum = np.diff(ip).astype(np.float64)                  # row sums of A (every stored entry has weight 1)
-        deg = dsum - has_loop                                  # diagonal of D - A
-        data = np.where(rows == ix, deg[rows], -1.0)
         with np.errstate(divide="ignore"):
             dh = 1.0 / np.sqrt(dsum)
         dh[np.isinf(dh)] = 0.0
-        data = data * dh[rows] * dh[ix]
-    return sparse.csr_matrix((data, ix.copy(), ip.copy()), shape=(n, n))
+        DH = sparse.diags(dh, 0, shape=(n, n), format="csr")
+        L = sparse.csr_matrix(DH @ (L @ DH), dtype=np.float64)
+    L.sort_indices()
+    return L
+
+
+def _nx_degree(G, A=None):
+    """networkx's unweighted ``G.degree()``: number of incident edges, a self loop counted twice (geometry.py:46)."""
+    if not isinstance(G, ManifoldGraph):
+        return np.array(list(dict(G.degree()).values()), dtype=np.float64)
+    A = G.scipy_adjacency() if A is None else A
+    n = A.shape[0]
+    rows = np.repeat(np.arange(n), np.diff(A.indptr))
+    has_loop = np.zeros(n, dtype=bool)
+    has_loop[rows[rows == A.indices]] = True
+    return (np.diff(A.indptr) + has_loop).astype(np.float64)
 
 
 def compute_connection_laplacian(G, R, normalization=None):
     """Connection Laplacian as scipy sparse (geometry.py:14-52): kron(L, 1_{dxd}) .* R; ``normalization='rw'`` multiplies
     row block i by 1 / deg_i with networkx's degree (a self loop counts twice, geometry.py:45-50)."""
     from scipy import sparse
-    ip, ix, n = _csr_host(G)
+    n = len(G)
     dim = R.shape[0] // n
     L = compute_laplacian(G)
     Lc = sparse.kron(L, np.ones([dim, dim])).multiply(R)
     if normalization == "rw":
-        rows = np.repeat(np.arange(n), np.diff(ip))
-        has_loop = np.zeros(n, dtype=bool)
-        has_loop[rows[rows == ix]] = True
-        deg = (np.diff(ip) + has_loop).astype(np.float64)      # nx degree: neighbours + 2 for the self loop
+        deg = _nx_degree(G)
         with np.errstate(divide="ignore"):
             deg_inv = 1.0 / deg
         deg_inv[np.isinf(deg_inv)] = 0
@@ -382,7 +400,12 @@ def compute_spectrum(laplacian, n_eigenpairs=None, dtype=None, tol=1e-12):
                   torch.from_numpy(B.indices.astype(np.int32)).to(dev), vals)
     # Gershgorin bound for symmetric matrices: max absolute row sum
     hi = float(abs(sparse.csr_matrix(laplacian)).sum(1).max())
-    evals, evecs = smallest_eigenpairs(A, n_eigenpairs, upper_bound=hi, lower_bound=min(0.0, -1e-12 * hi), tol=tol)
+    st = {}
+    evals, evecs = smallest_eigenpairs(A, n_eigenpairs, upper_bound=hi, lower_bound=min(0.0, -1e-12 * hi), tol=tol, stats=st)
+    if not st.get("converged", True):
+        # scipy's eigsh raises ArpackNoConvergence here (geometry.py:73)
+        raise RuntimeError("compute_spectrum: eigensolver did not converge (max residual %.3e > %.3e)" %
+                           (st["residual_max"], st["tol_abs"]))
     evecs = evecs.cpu().numpy() * np.sqrt(N)
     return evals.cpu().numpy().view(_Tensor), evecs.view(_Tensor)
 

@@ -48,10 +48,23 @@ def _node_rows_device(data, node_ind):
 
 
 def _as_node_indices(test_ind, n):
+    """Node indices as the NumPy-based reference would resolve them (main.py:31,104): negative indices wrap, anything
+    outside [-n, n) raises IndexError, a boolean mask must have n entries.  The device gather kernels do no bounds checks,
+    so nothing unvalidated may reach them."""
     a = np.asarray(test_ind)
     if a.dtype == bool:
-        return np.nonzero(a.reshape(-1))[0]
-    return a.reshape(-1).astype(np.int64)
+        a = a.reshape(-1)
+        if a.size != n:
+            raise IndexError("boolean index did not match indexed array along axis 0; size of axis is %d but size of "
+                             "corresponding boolean axis is %d" % (n, a.size))
+        return np.nonzero(a)[0]
+    if a.size and a.dtype.kind not in "iu":
+        raise IndexError("arrays used as indices must be of integer (or boolean) type")
+    a = a.reshape(-1).astype(np.int64)
+    bad = (a < -n) | (a >= n)
+    if bad.any():
+        raise IndexError("index %d is out of bounds for axis 0 with size %d" % (int(a[bad][0]), n))
+    return np.where(a < 0, a + n, a)
 
 
 def _rows_of(data, name, node_ind):

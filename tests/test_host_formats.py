@@ -67,3 +67,53 @@ def test_load_mesh(tmp_path):
             rv, rf = mod.load_mesh(name, folder="/root/reference/examples/data")
             ov, of = load_mesh(name, folder="/root/reference/examples/data")
             assert np.array_equal(rv, ov) and np.array_equal(rf, of)
+
+
+def test_laplacian_loop_free_and_weighted_graphs():
+    """Round-1 advisor finding: graphs WITHOUT self loops and graphs WITH edge weights (the reference's typ='affinity',
+    geometry.py:114-118) must give networkx's Laplacians, not the pipeline's unit-weight pattern."""
+    import networkx as nx
+    from scipy import sparse
+    from rvgp_b200 import geometry as geo
+    for G in (nx.path_graph(4), nx.cycle_graph(7), nx.star_graph(5)):
+        L = geo.compute_laplacian(G)
+        assert abs(L - sparse.csr_matrix(nx.laplacian_matrix(G), dtype=np.float64)).max() == 0.0
+        Ln = geo.compute_laplacian(G, normalization=True)
+        assert abs(Ln - sparse.csr_matrix(nx.normalized_laplacian_matrix(G), dtype=np.float64)).max() < 1e-15
+        assert np.allclose(Ln.diagonal(), 1.0)
+    X = np.random.default_rng(3).normal(size=(40, 3))
+    X /= np.linalg.norm(X, axis=1, keepdims=True)
+    from sklearn.metrics import pairwise_distances
+    A = np.exp(-pairwise_distances(X) ** 2 / (2 * 0.1 ** 2))       # geometry.py:115-117
+    G = nx.from_numpy_array(A)
+    L = geo.compute_laplacian(G)
+    ref = sparse.csr_matrix(nx.laplacian_matrix(G), dtype=np.float64)
+    assert abs(L - ref).max() <= 1e-15 * abs(ref).max()
+    Ln = geo.compute_laplacian(G, normalization=True)
+    refn = sparse.csr_matrix(nx.normalized_laplacian_matrix(G), dtype=np.float64)
+    assert abs(Ln - refn).max() < 1e-14
+    # connection Laplacian on a loop-free weighted graph, incl. 'rw' with networkx's unweighted degree (geometry.py:46)
+    dim = 2
+    R = sparse.kron(abs(ref), np.ones([dim, dim])).tocsr()
+    R.data = np.random.default_rng(4).normal(size=R.data.shape)
+    Lc = geo.compute_connection_laplacian(G, R, normalization="rw")
+    deg = np.array(list(dict(G.degree()).values()))
+    want = sparse.diags((1.0 / deg).repeat(dim), 0, format="csr") @ sparse.kron(ref, np.ones([dim, dim])).multiply(R)
+    assert abs(Lc - want).max() < 1e-14
+
+
+def test_node_index_validation():
+    """Round-1 advisor finding: user indices reach unchecked device gathers.  NumPy semantics: negatives wrap,
+    out-of-range raises IndexError, boolean masks must have n entries."""
+    from rvgp_b200.main import _as_node_indices
+    n = 10
+    np.testing.assert_array_equal(_as_node_indices([0, 3, -1, -10], n), [0, 3, 9, 0])
+    np.testing.assert_array_equal(_as_node_indices(np.array([True] + [False] * 8 + [True]), n), [0, 9])
+    np.testing.assert_array_equal(_as_node_indices([], n), [])
+    for bad in ([10], [-11], np.array([0, 99])):
+        with pytest.raises(IndexError):
+            _as_node_indices(bad, n)
+    with pytest.raises(IndexError):
+        _as_node_indices(np.ones(9, dtype=bool), n)
+    with pytest.raises(IndexError):
+        _as_node_indices(np.array([0.5, 1.0]), n)

@@ -77,40 +77,14 @@ int rvgp_cheb_filter_f64(rvgp_handle_t h, int nbrows, int d, const int32_t* indp
                          const double* vals, double* V, int64_t ldv, double* work0, double* work1,
                          int64_t ldw, int ncols, int degree, double lo_spec, double lo_cut, double hi);
 
-/* ---- K9 v2: shared-memory-staged SpMM.  rvgp_bsr_tile_plan lists, for every tile of TR consecutive block rows,
- * the unique neighbour nodes (ucols, padded to ucap per tile; tile_u = count) and rewrites each entry's column as
- * a 16-bit index into that list (lidx).  info (device int32[3]): [0] max unique per tile, [1] != 0 plan invalid
- * (keep using rvgp_bsr_spmm_f64), [2] max entries per tile.  rvgp_bsr_spmm_tiled_f64 has the contract of
- * rvgp_bsr_spmm_f64 but stages X rows and block values through shared memory with cp.async.bulk; it needs even
- * ncols, even ldx and 16-byte aligned X / vals.  rvgp_cheb_filter_tiled_f64 = rvgp_cheb_filter_f64 on top of it
- * (work0..2: three CONTIGUOUS (nrows x ncols) scratch panels). */
-int rvgp_bsr_tile_plan(rvgp_handle_t h, int nbrows, const int32_t* indptr, const int32_t* indices, int TR, int ucap,
-                       int32_t* tile_u, int32_t* ucols, uint16_t* lidx, int32_t* info);
-int rvgp_bsr_spmm_tiled_f64(rvgp_handle_t h, int nbrows, int d, int TR, int ucap, int umax, int nemax,
-                            const int32_t* indptr, const int32_t* tile_u, const int32_t* ucols, const uint16_t* lidx,
-                            const double* vals, const double* X, int64_t ldx, const double* W, int64_t ldw, double* Y,
-                            int64_t ldy, int ncols, double alpha, double beta, double gamma);
-int rvgp_cheb_filter_tiled_f64(rvgp_handle_t h, int nbrows, int d, int TR, int ucap, int umax, int nemax,
-                               const int32_t* indptr, const int32_t* tile_u, const int32_t* ucols, const uint16_t* lidx,
-                               const double* vals, double* V, int64_t ldv, double* work0, double* work1, double* work2,
-                               int ncols, int degree, double lo_spec, double lo_cut, double hi);
-
-/* ---- K9 v3: row-group merged SpMM.  R (4 or 8) consecutive block rows are processed together over the UNION of
- * their column lists (uent: int32 pairs (column, R-bit row mask); gptr: ngroups+1 offsets), so one gather of a
- * neighbour's X rows serves every row that stores it.  rvgp_bsr_merge_plan is called twice: first with uent == NULL
- * (fills gptr; gptr[ngroups] = number of union entries), then with uent allocated.  Same contract / alignment needs
- * as the 128-bit path of rvgp_bsr_spmm_f64; d = -2 selects ROT2 storage. */
+/* ---- row-group merge plan (input of the K9 v4 k-step plan below).  R (4 or 8) consecutive block rows are grouped and
+ * the UNION of their sorted column lists is formed (uent: int32 pairs (column, R-bit row mask); gptr: ngroups+1 offsets).
+ * rvgp_bsr_merge_plan is called twice: first with uent == NULL (fills gptr; gptr[ngroups] = number of union entries),
+ * then with uent allocated.  (The measured-and-rejected K9 v2 / v3 kernels that also consumed such plans live in
+ * tools/experiments/, outside the product library.) */
 int rvgp_bsr_merge_plan(rvgp_handle_t h, int nbrows, const int32_t* indptr, const int32_t* indices, int R,
                         int32_t* gptr, int32_t* uent, void* workspace, int64_t workspace_bytes);
 int64_t rvgp_bsr_merge_plan_workspace_bytes(int nbrows, int R);
-int rvgp_bsr_spmm_merged_f64(rvgp_handle_t h, int nbrows, int d, int R, const int32_t* indptr, const int32_t* indices,
-                             const int32_t* gptr, const int32_t* uent, const double* vals, const double* X, int64_t ldx,
-                             const double* W, int64_t ldw, double* Y, int64_t ldy, int ncols, double alpha, double beta,
-                             double gamma);
-int rvgp_cheb_filter_merged_f64(rvgp_handle_t h, int nbrows, int d, int R, const int32_t* indptr, const int32_t* indices,
-                                const int32_t* gptr, const int32_t* uent, const double* vals, double* V, int64_t ldv,
-                                double* work0, double* work1, int64_t ldw, int ncols, int degree, double lo_spec,
-                                double lo_cut, double hi);
 
 /* ---- K9 v4: row-group SpMM on the FP64 tensor path (mma.sync.m8n8k4.f64), d in {1, 2}.  Groups of 8/d consecutive
  * block rows are the 8 MMA rows; the union of their column lists (rvgp_bsr_merge_plan with R = 8/d) is cut into k-steps of

@@ -1,4 +1,5 @@
-"""Build librvgp_b200.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels with the repo)."""
+"""Build librvgp_b200.so in-tree with nvcc for sm_100a.  No JIT cache: the built rvgp_b200/lib/librvgp_b200.so is git-ignored
+(history stays source-only) but is part of the gpurun snapshot, so it travels to the GPU box with the working tree."""
 import os
 import subprocess
 import sys
@@ -51,7 +52,7 @@ def build(verbose=False, force=False):
                     print("   ", l.strip())
     objs = [os.path.join(OBJ, s[:-3] + ".o") for s in srcs]
     if jobs or not os.path.exists(LIB):
-        subprocess.check_call([NVCC, "-shared", "-o", LIB] + objs + ["-lcudart"])
+        subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + ["-lcudart"])
     return LIB
 
 

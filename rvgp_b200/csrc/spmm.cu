@@ -449,13 +449,6 @@ extern "C" int rvgp_bsr_compress_rot2(rvgp_handle_t hh, int64_t nnzb, const doub
     return RVGP_OK;
 }
 
-namespace rvgp {
-int spmm_tiled_dispatch(Handle* h, int nbrows, int d, int TR, int ucap, int umax, int nemax, const int* indptr,
-                        const int* tile_u, const int* ucols, const unsigned short* lidx, const double* vals,
-                        const double* X, int64_t ldx, const double* W, int64_t ldw, double* Y, int64_t ldy, int ncols,
-                        double alpha, double beta, double gamma);
-}
-
 // Scaled Chebyshev filter (Zhou & Saad, "A Chebyshev-Davidson algorithm", Alg. 3.1 form):
 //   e = (hi - lo_cut)/2, c = (hi + lo_cut)/2, sigma_1 = e / (lo_spec - c), tau = 2 / sigma_1
 //   Y_1     = (A V - c V) * sigma_1 / e
@@ -503,39 +496,6 @@ extern "C" int rvgp_cheb_filter_f64(rvgp_handle_t hh, int nbrows, int d, const i
         RVGP_CUDA_OK(h, cudaMemcpy2DAsync(V, ldv * sizeof(double), buf[slot], ld[slot] * sizeof(double),
                                           (size_t)ncols * sizeof(double), (size_t)nbrows * (d < 0 ? -d : d),
                                           cudaMemcpyDeviceToDevice, h->stream));
-    }
-    return RVGP_OK;
-}
-
-namespace rvgp {
-int spmm_merged_dispatch(Handle* h, int nbrows, int d, int R, const int* indptr, const int* indices, const int* gptr,
-                         const int* uent, const double* vals, const double* X, int64_t ldx, const double* W, int64_t ldw,
-                         double* Y, int64_t ldy, int ncols, double alpha, double beta, double gamma);
-}
-
-// Same filter through the row-group merged SpMM (rvgp_bsr_spmm_merged_f64, spmm_merged.cu).
-extern "C" int rvgp_cheb_filter_merged_f64(rvgp_handle_t hh, int nbrows, int d, int R, const int32_t* indptr,
-                                           const int32_t* indices, const int32_t* gptr, const int32_t* uent,
-                                           const double* vals, double* V, int64_t ldv, double* work0, double* work1,
-                                           int64_t ldw, int ncols, int degree, double lo_spec, double lo_cut, double hi) {
-    Handle* h = H(hh);
-    RVGP_REQUIRE(h, degree >= 0, "cheb_filter: degree >= 0");
-    RVGP_REQUIRE(h, hi > lo_cut && lo_cut > lo_spec, "cheb_filter: need lo_spec < lo_cut < hi");
-    if (degree == 0 || nbrows == 0) return RVGP_OK;
-    const int dd = d < 0 ? -d : d;
-    double* buf[3] = {V, work0, work1};
-    int64_t ld[3] = {ldv, ldw, ldw};
-    int slot = 0;
-    auto apply = [&](const double* X, int64_t ldx, const double* W, int64_t ldw_, double* Y, int64_t ldy, double a, double b,
-                     double g) {
-        return spmm_merged_dispatch(h, nbrows, d, R, indptr, indices, gptr, uent, vals, X, ldx, W, ldw_, Y, ldy, ncols, a, b, g);
-    };
-    int rc = cheb_recurrence(h, apply, (int64_t)nbrows * dd, buf, ld, ncols, degree, lo_spec, lo_cut, hi, &slot);
-    if (rc) return rc;
-    if (slot != 0) {
-        RVGP_CUDA_OK(h, cudaMemcpy2DAsync(V, ldv * sizeof(double), buf[slot], ld[slot] * sizeof(double),
-                                          (size_t)ncols * sizeof(double), (size_t)nbrows * dd, cudaMemcpyDeviceToDevice,
-                                          h->stream));
     }
     return RVGP_OK;
 }
@@ -591,35 +551,5 @@ extern "C" int rvgp_cheb_filter_mma_f64(rvgp_handle_t hh, int nbrows, int d, con
                                           (size_t)ncols * sizeof(double), (size_t)nbrows * d, cudaMemcpyDeviceToDevice,
                                           h->stream));
     }
-    return RVGP_OK;
-}
-
-// Same filter through the shared-memory-staged SpMM (rvgp_bsr_spmm_tiled_f64).  The panel is first copied into a
-// CONTIGUOUS scratch panel so that every staged neighbour is one bulk copy of d*ncols*8 bytes; work0..work2 are three
-// (nrows x ncols) contiguous scratch panels.
-extern "C" int rvgp_cheb_filter_tiled_f64(rvgp_handle_t hh, int nbrows, int d, int TR, int ucap, int umax, int nemax,
-                                          const int32_t* indptr, const int32_t* tile_u, const int32_t* ucols,
-                                          const uint16_t* lidx, const double* vals, double* V, int64_t ldv, double* work0,
-                                          double* work1, double* work2, int ncols, int degree, double lo_spec,
-                                          double lo_cut, double hi) {
-    Handle* h = H(hh);
-    RVGP_REQUIRE(h, degree >= 0, "cheb_filter: degree >= 0");
-    RVGP_REQUIRE(h, hi > lo_cut && lo_cut > lo_spec, "cheb_filter: need lo_spec < lo_cut < hi");
-    if (degree == 0 || nbrows == 0) return RVGP_OK;
-    const int64_t nrows = (int64_t)nbrows * d;
-    RVGP_CUDA_OK(h, cudaMemcpy2DAsync(work0, (size_t)ncols * sizeof(double), V, ldv * sizeof(double),
-                                      (size_t)ncols * sizeof(double), (size_t)nrows, cudaMemcpyDeviceToDevice, h->stream));
-    double* buf[3] = {work0, work1, work2};
-    int64_t ld[3] = {ncols, ncols, ncols};
-    int slot = 0;
-    auto apply = [&](const double* X, int64_t ldx, const double* W, int64_t ldw_, double* Y, int64_t ldy, double a, double b,
-                     double g) {
-        return spmm_tiled_dispatch(h, nbrows, d, TR, ucap, umax, nemax, indptr, tile_u, ucols, lidx, vals, X, ldx, W, ldw_, Y,
-                                   ldy, ncols, a, b, g);
-    };
-    int rc = cheb_recurrence(h, apply, nrows, buf, ld, ncols, degree, lo_spec, lo_cut, hi, &slot);
-    if (rc) return rc;
-    RVGP_CUDA_OK(h, cudaMemcpy2DAsync(V, ldv * sizeof(double), buf[slot], (size_t)ncols * sizeof(double),
-                                      (size_t)ncols * sizeof(double), (size_t)nrows, cudaMemcpyDeviceToDevice, h->stream));
     return RVGP_OK;
 }

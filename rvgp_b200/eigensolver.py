@@ -90,12 +90,6 @@ class BsrMatrix:
                    X, I64(X.stride(0)), W, I64(W.stride(0) if W is not None else 0), Y, I64(Y.stride(0)),
                    int(ncols), float(alpha), float(beta), float(gamma))
             return Y
-        if self._merged_ok(ncols, X, Y, W):
-            mp = self.merged
-            h.call("rvgp_bsr_spmm_merged_f64", self.nbrows, dc, mp["R"], self.indptr, ix, mp["gptr"], mp["uent"], vl,
-                   X, I64(X.stride(0)), W, I64(W.stride(0) if W is not None else 0), Y, I64(Y.stride(0)),
-                   int(ncols), float(alpha), float(beta), float(gamma))
-            return Y
         h.call("rvgp_bsr_spmm_f64", self.nbrows, dc, self.indptr, ix, vl,
                X, I64(X.stride(0)), W, I64(W.stride(0) if W is not None else 0), Y, I64(Y.stride(0)),
                int(ncols), float(alpha), float(beta), float(gamma))
@@ -190,7 +184,7 @@ class BsrMatrix:
                float(beta), float(gamma), int(bool(reverse)))
         return Yn
 
-    # ---- row-group merged variant (K9 v3) -------------------------------------------------------------------
+    # ---- row-group merge plan (union column lists; input of the MMA k-step plan) --------------------------------
     def build_merge_plan(self, R=4, h=None):
         """Union column lists of groups of R consecutive block rows (rvgp_bsr_merge_plan)."""
         plans = self.__dict__.setdefault("_mplans", {})
@@ -208,67 +202,6 @@ class BsrMatrix:
         h.call("rvgp_bsr_merge_plan", self.nbrows, self.indptr, self.indices, int(R), gptr, uent, ws, I64(wsb))
         plans[R] = dict(R=int(R), gptr=gptr, uent=uent, total=total, reuse=self.nnzb / max(1, total))
         return plans[R]
-
-    def enable_merged(self, R=4, h=None):
-        """Route spmm / cheb_filter through the merged kernel when the buffers allow it."""
-        self.merged = self.build_merge_plan(R, h=h)
-        return self.merged
-
-    def _merged_ok(self, ncols, *tensors):
-        if getattr(self, "merged", None) is None or ncols % 2 or self.d > 3:
-            return False
-        return all(t is None or (t.stride(0) % 2 == 0 and t.data_ptr() % 16 == 0) for t in tensors)
-
-    # ---- shared-memory-staged variant (K9 v2) ---------------------------------------------------------
-    def build_plan(self, TR, ucap=None, h=None):
-        """Tile plan for rvgp_bsr_spmm_tiled_f64; returns the plan dict or None when the pattern is not local
-        enough (then the gather kernel keeps being used)."""
-        key = int(TR)
-        plans = self.__dict__.setdefault("_plans", {})
-        if key in plans:
-            return plans[key]
-        h = h or get_handle(self.indptr.device.index)
-        dev = self.indptr.device
-        if ucap is None:
-            ucap = min(1024, 16 * TR)
-        ntiles = (self.nbrows + TR - 1) // TR
-        tile_u = torch.empty(ntiles, dtype=torch.int32, device=dev)
-        ucols = torch.empty(ntiles * ucap, dtype=torch.int32, device=dev)
-        lidx = torch.empty(max(1, self.nnzb), dtype=torch.int16, device=dev)
-        info = torch.zeros(3, dtype=torch.int32, device=dev)
-        h.call("rvgp_bsr_tile_plan", self.nbrows, self.indptr, self.indices, int(TR), int(ucap), tile_u, ucols, lidx, info)
-        umax, invalid, nemax = [int(v) for v in info.cpu().tolist()]
-        plan = None
-        if not invalid:
-            # shared memory is sized for the 97th percentile of unique neighbours per tile; the few heavier tiles
-            # (Morton-curve jumps) gather from global memory inside the same kernel
-            tu = tile_u.cpu().numpy()
-            usoft = int(min(umax, (int(np.percentile(tu, 97)) + 3) // 4 * 4))
-            plan = dict(TR=int(TR), ucap=int(ucap), umax=umax, usoft=usoft, nemax=nemax, tile_u=tile_u, ucols=ucols,
-                        lidx=lidx, umean=float(tu.mean()), heavy_frac=float((tu > usoft).mean()))
-        plans[key] = plan
-        return plan
-
-    def tiled_smem_bytes(self, plan, ncols):
-        d = self.d
-        return (32 + plan["usoft"] * d * ncols * 8 + (plan["nemax"] * d * d * 8 if self.vals is not None else 0)
-                + ((plan["nemax"] + 7) // 8 * 8) * 2 + plan["ucap"] * 4)
-
-    def choose_plan(self, ncols, budget=100 * 1024, h=None):
-        """Largest tile whose staged working set leaves >= 2 CTAs per SM."""
-        for TR in (64, 32, 16, 8):
-            plan = self.build_plan(TR, h=h)
-            if plan is not None and self.tiled_smem_bytes(plan, ncols) <= budget:
-                return plan
-        return None
-
-    def spmm_tiled(self, plan, X, Y, alpha=1.0, beta=0.0, gamma=0.0, W=None, h=None):
-        h = h or get_handle(X.device.index)
-        h.call("rvgp_bsr_spmm_tiled_f64", self.nbrows, self.d, plan["TR"], plan["ucap"], plan["usoft"], plan["nemax"],
-               self.indptr, plan["tile_u"], plan["ucols"], plan["lidx"], self.vals, X, I64(X.stride(0)), W,
-               I64(W.stride(0) if W is not None else 0), Y, I64(Y.stride(0)), int(X.shape[1]), float(alpha),
-               float(beta), float(gamma))
-        return Y
 
     row_offset = 0          # global row of local row 0 (non-zero only for row-sharded operators)
 
@@ -293,12 +226,6 @@ class BsrMatrix:
             mp = self.mma
             h.call("rvgp_cheb_filter_mma_f64", self.nbrows, self.d, mp["kptr"], mp["kcols"], mp["afrag"], 0,
                    Vp, I64(Vp.stride(0)), w0, w1, None, I64(w0.stride(0)), int(ncols), int(degree), float(lo_spec),
-                   float(lo_cut), float(hi))
-            return
-        if self._merged_ok(ncols, Vp, w0, w1):
-            mp = self.merged
-            h.call("rvgp_cheb_filter_merged_f64", self.nbrows, dc, mp["R"], self.indptr, ix, mp["gptr"], mp["uent"], vl,
-                   Vp, I64(Vp.stride(0)), w0, w1, I64(w0.stride(0)), int(ncols), int(degree), float(lo_spec),
                    float(lo_cut), float(hi))
             return
         h.call("rvgp_cheb_filter_f64", self.nbrows, dc, self.indptr, ix, vl, Vp, I64(Vp.stride(0)),

@@ -166,45 +166,6 @@ def test_eigensolver_matches_reference_arpack(case):
             assert subspace_angle_max(Phi[:, s], ref[:, s]) < 1e-6, (which, s)
 
 
-@pytest.mark.parametrize("case", ["sphere_n2000_k50", "flat3torus_R6_n900_k24", "torus_n600_k20"])
-@pytest.mark.parametrize("ncols", [2, 16, 32, 50, 64])
-@pytest.mark.parametrize("TR", [8, 16, 32])
-def test_spmm_tiled_matches_scipy(case, ncols, TR):
-    """K9 v2 (TMA-staged tiles) against SciPy, on matrices in their ORIGINAL (non-local) order as well: the plan only
-    needs ucap to hold the tile's unique neighbours."""
-    g = load_golden(case)
-    for which in ("Lc", "L"):
-        A, S = _bsr_from_golden(g, which)
-        plan = A.build_plan(TR, ucap=min(1024, 40 * TR))
-        assert plan is not None
-        if A.tiled_smem_bytes(plan, ncols) > 200 * 1024:
-            continue
-        rng = np.random.default_rng(2)
-        X = rng.normal(size=(A.nrows, ncols)); W = rng.normal(size=(A.nrows, ncols))
-        Xd, Wd = torch.from_numpy(X).to(_dev()), torch.from_numpy(W).to(_dev())
-        Yd = torch.full_like(Xd, 7.0)
-        A.spmm_tiled(plan, Xd, Yd)
-        ref = S @ X
-        assert np.abs(Yd.cpu().numpy() - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max())
-        A.spmm_tiled(plan, Xd, Yd, alpha=0.7, beta=-1.3, gamma=0.25, W=Wd)
-        ref2 = 0.7 * ref - 1.3 * X + 0.25 * W
-        assert np.abs(Yd.cpu().numpy() - ref2).max() <= 1e-13 * max(1.0, np.abs(ref2).max())
-        # strided input (panel view of a wider block vector): non-contiguous staging path
-        big = torch.zeros((A.nrows, 2 * ncols + 6), dtype=torch.float64, device=_dev())
-        big[:, 4:4 + ncols] = Xd
-        A.spmm_tiled(plan, big[:, 4:4 + ncols], Yd)
-        assert np.abs(Yd.cpu().numpy() - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max())
-
-
-def test_spmm_tiled_rejects_unaligned():
-    g = load_golden("torus_n600_k20")
-    A, S = _bsr_from_golden(g, "Lc")
-    plan = A.build_plan(16, ucap=640)
-    X = torch.zeros((A.nrows, 7), dtype=torch.float64, device=_dev())
-    with pytest.raises(ValueError):
-        A.spmm_tiled(plan, X, torch.empty_like(X))
-
-
 @pytest.mark.parametrize("ncols", [2, 16, 32, 64])
 def test_spmm_rot2_storage(ncols):
     """ROT2 (a, b, flip) storage of the 2x2 connection blocks gives the same product as the plain blocks."""
@@ -223,31 +184,6 @@ def test_spmm_rot2_storage(ncols):
     vals = torch.from_numpy(g["Lc_data"].copy()); vals[5, 0, 1] += 0.3
     B = BsrMatrix(A.nbrows, 2, A.indptr, A.indices, vals.to(_dev()))
     assert not B.compress_rot2() and B.d_code == 2
-
-
-@pytest.mark.parametrize("case", ["sphere_n2000_k50", "flat3torus_R6_n900_k24", "torus_n600_k20"])
-@pytest.mark.parametrize("ncols", [2, 16, 32, 64])
-@pytest.mark.parametrize("R", [4, 8])
-def test_spmm_merged_matches_scipy(case, ncols, R):
-    """K9 v3 (row-group merged gathers) == SciPy for Lc (plain and ROT2 storage) and the pattern-mode L."""
-    g = load_golden(case)
-    for which in ("Lc", "L"):
-        A, S = _bsr_from_golden(g, which)
-        mp = A.enable_merged(R)
-        assert mp["total"] <= A.nnzb and mp["reuse"] >= 1.0
-        rng = np.random.default_rng(3)
-        X = rng.normal(size=(A.nrows, ncols)); W = rng.normal(size=(A.nrows, ncols))
-        Xd, Wd = torch.from_numpy(X).to(_dev()), torch.from_numpy(W).to(_dev())
-        for rot in ((False, True) if (which == "Lc" and A.d == 2) else (False,)):
-            if rot:
-                assert A.compress_rot2()
-            Yd = torch.full_like(Xd, 7.0)
-            A.spmm(Xd, Yd)
-            ref = S @ X
-            assert np.abs(Yd.cpu().numpy() - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max())
-            A.spmm(Xd, Yd, alpha=0.7, beta=-1.3, gamma=0.25, W=Wd)
-            ref2 = 0.7 * ref - 1.3 * X + 0.25 * W
-            assert np.abs(Yd.cpu().numpy() - ref2).max() <= 1e-13 * max(1.0, np.abs(ref2).max())
 
 
 @pytest.mark.parametrize("case", ["sphere_n2000_k50", "flat3torus_R6_n900_k24", "torus_n600_k20"])

@@ -209,6 +209,11 @@ int64_t rvgp_knn_grid_workspace_bytes(int n, int D, const double* lo, const doub
 int rvgp_knn_to_csr(rvgp_handle_t h, const int32_t* knn, int n, int k, int32_t* indptr, int32_t* indices,
                     int32_t* nnz_out, void* workspace, int64_t workspace_bytes);
 int64_t rvgp_knn_to_csr_workspace_bytes(int n, int k);
+/* typ='affinity' graph of manifold_graph (geometry.py:114-118): dense Gaussian-kernel weights
+ * A[i][j] = exp(-dist(i,j)^2 / (2 sigma^2)) with sklearn's pairwise_distances expansion, diagonal distance forced to 0.
+ * A: n x n row-major; workspace: n doubles; n <= 65535. */
+int rvgp_affinity_f64(rvgp_handle_t h, const double* X, int n, int D, double sigma, double* A, double* workspace);
+
 /* locality (Morton) ordering of the points and symmetric permutation of a CSR pattern (eigensolver layout) */
 int rvgp_morton_order(rvgp_handle_t h, const double* X, int n, int D, int32_t* order, int32_t* inv,
                       void* workspace, int64_t workspace_bytes);

@@ -246,3 +246,49 @@ extern "C" int rvgp_csr_permute(rvgp_handle_t hh, int n, const int32_t* indptr, 
     RVGP_LAUNCH_OK(h, "perm_fill_kernel");
     return RVGP_OK;
 }
+
+// ---- typ='affinity' graph (geometry.py:114-118): dense Gaussian-kernel weights --------------------------------------------
+//   A[i][j] = exp(-dist(i,j)^2 / (2 sigma^2)),  dist = sklearn.metrics.pairwise_distances(X) (euclidean_distances expansion:
+//   sqrt(max(-2 x.y + |x|^2 + |y|^2, 0)), diagonal forced to 0), squared again like the reference's `** 2`.
+// One thread per (i, j); the row of X for i is staged in shared memory.  O(n^2 D) by definition of this graph type.
+namespace rvgp {
+__global__ void affinity_norms_kernel(const double* __restrict__ X, int n, int D, double* __restrict__ xx) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = 0.0;
+    for (int k = 0; k < D; ++k) { const double v = X[i * D + k]; s = __dadd_rn(s, __dmul_rn(v, v)); }
+    xx[i] = s;
+}
+
+__global__ void __launch_bounds__(256)
+affinity_kernel(const double* __restrict__ X, const double* __restrict__ xx, int n, int D, double two_sigma2,
+                double* __restrict__ A) {
+    extern __shared__ double xi[];
+    const int i = blockIdx.y;
+    for (int k = threadIdx.x; k < D; k += blockDim.x) xi[k] = X[(int64_t)i * D + k];
+    __syncthreads();
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    double dot = 0.0;
+    for (int k = 0; k < D; ++k) dot = fma(xi[k], __ldg(X + (int64_t)j * D + k), dot);
+    double d2 = __dadd_rn(__dadd_rn(-2.0 * dot, xx[i]), xx[j]);
+    d2 = d2 > 0.0 ? d2 : 0.0;
+    double dist = (i == j) ? 0.0 : sqrt(d2);
+    A[(int64_t)i * n + j] = exp(-__dmul_rn(dist, dist) / two_sigma2);
+}
+}  // namespace rvgp
+
+// Dense affinity matrix A (n x n, row-major) of the reference's typ='affinity' graph; workspace: n doubles.
+extern "C" int rvgp_affinity_f64(rvgp_handle_t hh, const double* X, int n, int D, double sigma, double* A, double* workspace) {
+    Handle* h = H(hh);
+    RVGP_REQUIRE(h, n >= 0 && D >= 1 && D <= 4096, "affinity: need 1 <= D <= 4096");
+    RVGP_REQUIRE(h, sigma > 0.0, "affinity: sigma must be positive");
+    if (n == 0) return RVGP_OK;
+    affinity_norms_kernel<<<cdiv(n, 256), 256, 0, h->stream>>>(X, n, D, workspace);
+    RVGP_LAUNCH_OK(h, "affinity_norms_kernel");
+    dim3 grid(cdiv(n, 256), n);
+    RVGP_REQUIRE(h, n <= 65535, "affinity: n must be <= 65535 (dense n x n graph)");
+    affinity_kernel<<<grid, 256, (size_t)D * sizeof(double), h->stream>>>(X, workspace, n, D, 2.0 * sigma * sigma, A);
+    RVGP_LAUNCH_OK(h, "affinity_kernel");
+    return RVGP_OK;
+}

@@ -17,7 +17,68 @@ import torch
 
 from . import geometry as geo
 from .eigensolver import BsrMatrix, smallest_eigenpairs, smallest_eigenpairs_paired
+from .krylov import krylov_eigenpairs
 from .smoothing import vector_diffusion_device
+from . import _nvtx
+
+
+def _coarse_spectrum(Xd, n_neighbors, j_max, ratio=16, n_min=20000, seed=0):
+    """Eigenvalue estimates of the FINE graph Laplacian from a random SUBSAMPLE of the cloud.  For a kNN graph with the same
+    n_neighbors the low spectrum depends on the index only through j / n (continuum limit: lambda_j ~ (j / n)^(2/d) on a
+    d-manifold), so lambda_fine(J) ~ lambda_coarse(J * n_c / n) (measured on the C2 torus: within 1-3 % for ratios 4 and 8).
+    Only used to place the Chebyshev filter of the Krylov eigensolver (krylov.py); a wrong estimate costs time, not accuracy.
+    Returns a function J -> estimate, or None when the cloud is too small to subsample."""
+    n = Xd.shape[0]
+    n_c = max(min(int(n_min), n // 4), n // int(ratio))
+    if n_c < 2000:
+        return None
+    g = torch.Generator().manual_seed(int(seed))
+    idx = torch.sort(torch.randperm(n, generator=g)[:n_c]).values.to(Xd.device)
+    Xc = Xd.index_select(0, idx).contiguous()
+    knn = geo.knn_device(Xc, n_neighbors)
+    ip, ix = geo.knn_to_csr_device(knn)
+    order, inv = geo.morton_order_device(Xc)
+    pip, pix = geo.csr_permute_device(ip, ix, order, inv)
+    hi = 2.0 * (int((ip[1:] - ip[:-1]).max().item()) - 1)
+    r = n / float(n_c)
+    kc = min(n_c // 8, int(np.ceil(j_max / r)) + 4)
+    ev, _ = smallest_eigenpairs(BsrMatrix(n_c, 1, pip, pix, None), kc, upper_bound=hi, tol=1e-7)
+    ev = ev.cpu().numpy()
+
+    def lam(J):
+        jc = min(max(J / r, 1.0), float(len(ev)) - 1e-9)
+        lo = int(np.floor(jc))
+        f = jc - lo
+        return float(ev[lo - 1] * (1.0 - f) + ev[min(lo, len(ev) - 1)] * f)
+
+    return lam
+
+
+def _spectrum_from_scalar(evals_L, dim_man):
+    """Estimates for the connection Laplacian from the scalar spectrum: Weyl's law for a rank-d vector bundle gives
+    N_Lc(lambda) ~ d * N_L(lambda), i.e. lambda^Lc_J ~ lambda^L_(J/d) (C2 torus: within 2 % for J >= 20; curvature only
+    shifts the low end).  Beyond the computed scalar eigenvalues: lambda ~ J^(2/d) extrapolation."""
+    ev = np.asarray(evals_L, dtype=np.float64)
+
+    def lam(J):
+        j = max(J / float(dim_man), 2.0)
+        if j <= len(ev) - 1:
+            lo = int(np.floor(j))
+            f = j - lo
+            return float(ev[lo - 1] * (1.0 - f) + ev[lo] * f)
+        return float(ev[-1] * (j / len(ev)) ** (2.0 / dim_man))
+
+    return lam
+
+
+def _use_krylov(n, k, Nrows):
+    """Filtered block Lanczos (krylov.py) for large problems; ChFSI otherwise.  RVGP_EIGSOLVER = chfsi | krylov | auto."""
+    mode = os.environ.get("RVGP_EIGSOLVER", "auto")
+    if mode == "chfsi" or k >= Nrows // 8:
+        return False
+    if mode == "krylov":
+        return k >= 32
+    return n >= 100000 and k >= 128
 
 
 class _Dual:
@@ -75,6 +136,14 @@ class data:
             torch.cuda.synchronize(dev)
             return time.perf_counter()
 
+        def stage(name, _open=[False]):
+            """NVTX range per pipeline stage (closed by the next call; stage(None) closes the last one)."""
+            if _open[0]:
+                _nvtx.pop()
+            _open[0] = name is not None
+            if name is not None:
+                _nvtx.push(name)
+
         # multi-GPU: one process per GPU (torch.distributed); kNN queries and the eigensolver are row-sharded,
         # everything else is replicated (SURVEY.md section 8e)
         import torch.distributed as dist
@@ -91,6 +160,7 @@ class data:
         self.timings["h2d"] = tick() - t0
 
         say('Fit graph')
+        stage('graph')
         t0 = tick()
         if shard:
             q0, q1 = (n * rank) // world, (n * (rank + 1)) // world
@@ -104,6 +174,7 @@ class data:
         self.timings["graph"] = tick() - t0
 
         say('Fit tangent spaces')
+        stage('geodesic_neighbourhoods')
         t0 = tick()
         # ptu_dijkstra.tangent_frames(vertices, G, d=D, K=n_neighbors*frac)  (dataclass.py:35; K truncated to int)
         K = n_neighbors * frac_geodesic_neighbours
@@ -114,6 +185,7 @@ class data:
         max_row = graph.max_row
         seq, _ = geo.geodesic_neighbourhoods_device(graph.indptr, graph.indices, int(K), max_row)
         self.timings["geodesic"] = tick() - t0
+        stage('tangent_frames')
         t0 = tick()
         tangents, Sigma = geo.tangent_frames_device(Xd, seq, D)
         if explained_variance == 1.0:
@@ -128,12 +200,14 @@ class data:
         self.timings["tangent_frames"] = tick() - t0
 
         # locality ordering for the spectral stage (the heap emulation above needed the ORIGINAL numbering)
+        stage('morton_reorder')
         t0 = tick()
         order, inv = geo.morton_order_device(Xd)
         p_indptr, p_indices = geo.csr_permute_device(graph.indptr, graph.indices, order, inv)
         gauges_p = geo.gather_rows_device(gauges.reshape(n, D * dim_man), order).reshape(n, D, dim_man)
         self.timings["reorder"] = tick() - t0
 
+        stage('connections')
         t0 = tick()
         Lc_vals_p = geo.connections_device(gauges_p, p_indptr, p_indices)
         say('Fit connections')
@@ -167,8 +241,28 @@ class data:
 
         say('Compute eigendecompositions')
         hi = 2.0 * (max_row - 1)
+        stage('eig_L')
         t0 = tick()
         st_L, st_Lc = {}, {}
+        kry_L, kry_Lc = _use_krylov(n, k_L, N_L), _use_krylov(n, k_Lc, N_Lc)
+        paired = self.stats["paired"]
+
+        def solve_L(op, comm=None):
+            """Smallest k_L eigenpairs of the scalar Laplacian (geometry.py:66-80 on L)."""
+            lam = _coarse_spectrum(Xd, n_neighbors, 1.6 * k_L + 64) if kry_L else None
+            if lam is None:
+                return smallest_eigenpairs(op, k_L, upper_bound=hi, tol=eig_tol, stats=st_L, comm=comm)
+            J = max(1.5 * k_L, k_L + 64)
+            return krylov_eigenpairs(op, k_L, hi, cut=1.05 * lam(J), lam_k=lam(k_L), tol=eig_tol, stats=st_L, comm=comm)
+
+        def solve_Lc(op, evals_L_dev, comm=None, init_fn=None):
+            """Smallest k_Lc eigenpairs of the connection Laplacian (geometry.py:66-80 on Lc)."""
+            if not kry_Lc:
+                return eig_Lc(op, k_Lc, upper_bound=hi, tol=eig_tol, stats=st_Lc, comm=comm, init_fn=init_fn)
+            lam = _spectrum_from_scalar(evals_L_dev.cpu().numpy(), dim_man)
+            J = max(1.5 * k_Lc, k_Lc + 64 * (2 if paired else 1))
+            return krylov_eigenpairs(op, k_Lc, hi, cut=1.05 * lam(J), lam_k=lam(k_Lc), paired=paired, tol=eig_tol, stats=st_Lc,
+                                     comm=comm)
         if shard:
             from .distributed import HaloPlan, ShardedBsr, Comm, partition_rows
             comm = Comm()
@@ -182,11 +276,12 @@ class data:
             counts = [int(bounds[r + 1] - bounds[r]) for r in range(world)]
             self.stats["halo"] = dict(n_loc=plan.n_loc, n_halo=plan.n_halo, send=sum(plan.send_counts))
             try:
-                evals_L, U_loc = smallest_eigenpairs(S_L, k_L, upper_bound=hi, tol=eig_tol, stats=st_L, comm=comm)
+                evals_L, U_loc = solve_L(S_L, comm)
             finally:
                 S_L.close()                   # frees the cudaMalloc / CUDA-IPC halo buffers and the peer mappings
             U_L_p = comm.allgather_rows(U_loc, counts)
             self.timings["eig_L"] = tick() - t0
+            stage('eig_Lc')
             t0 = tick()
             r0, r1 = plan.r0, plan.r1
 
@@ -197,17 +292,18 @@ class data:
                         int(U.shape[1]), V, geo.I64(V.stride(0)), int(ncols))
 
             try:
-                evals_Lc, U_loc = eig_Lc(S_Lc, k_Lc, upper_bound=hi, tol=eig_tol, stats=st_Lc, comm=comm,
-                                         init_fn=lc_guess_loc if warm_start else None)
+                evals_Lc, U_loc = solve_Lc(S_Lc, evals_L, comm, lc_guess_loc if warm_start else None)
             finally:
                 S_Lc.close()
             U_Lc_p = comm.allgather_rows(U_loc, [c * dim_man for c in counts])
             del U_loc, S_L, S_Lc, plan
             self.timings["eig_Lc"] = tick() - t0
         else:
-            evals_L, U_L_p = smallest_eigenpairs(A_L, k_L, upper_bound=hi, tol=eig_tol, stats=st_L)
+            evals_L, U_L_p = solve_L(A_L)
             self.timings["eig_L"] = tick() - t0
+            stage('eig_Lc')
             t0 = tick()
+
             def lc_guess(V, U=U_L_p):
                 # smooth vector fields ~ scalar eigenfunctions x projected constant ambient directions
                 hh = geo.get_handle(dev.index)
@@ -215,8 +311,7 @@ class data:
                 hh.call("rvgp_lift_guess", gauges_eig, geo.I64(n), int(D), int(dim_man), U, geo.I64(U.stride(0)),
                         int(U.shape[1]), V, geo.I64(V.stride(0)), int(ncols))
 
-            evals_Lc, U_Lc_p = eig_Lc(A_eig, k_Lc, upper_bound=hi, tol=eig_tol, stats=st_Lc,
-                                      init_fn=lc_guess if warm_start else None)
+            evals_Lc, U_Lc_p = solve_Lc(A_eig, evals_L, None, lc_guess if warm_start else None)
             self.timings["eig_Lc"] = tick() - t0
         self.stats["eig_L"], self.stats["eig_Lc"] = st_L, st_Lc
         if self.stats["paired"]:
@@ -226,6 +321,7 @@ class data:
                                            geo.I64(U_Lc_p.stride(0)))
             del A_eig, gauges_eig
 
+        stage('lift')
         t0 = tick()
         # un-permute; scale by sqrt(#rows) (geometry.py:75); lift T u to ambient coordinates (dataclass.py:57-59)
         evecs_L = geo.gather_rows_device(U_L_p.contiguous(), inv)
@@ -240,6 +336,7 @@ class data:
         evecs_Lc = geo.gather_rows_device(lifted_p.reshape(n * D, kc), inv, block=D)
         del lifted_p
         self.timings["lift"] = tick() - t0
+        stage(None)
 
         # device-resident state used by smooth_vector_field / fit.  Only ONE copy of each eigenvector matrix is kept (C4:
         # evecs_Lc 12 GB + evecs_L 4 GB); the unit-norm Morton-ordered local-coordinate forms that the smoothing deflation
@@ -403,7 +500,10 @@ class data:
     def smooth_vector_field(self, t=100):
         """Smooth vector field over manifold (dataclass.py:105-120): heat diffusion with Lc for the direction
         and with L for the magnitude (smoothing.py:37-64)."""
-        if "vectors" in self._duals:
+        if "vectors" not in self._duals:
+            print('No vectors found. Nothing to smooth.')
+            return
+        with _nvtx.stage("smooth_vector_field"):
             n, D, d = self.n, self._Xd.shape[1], self.dim_man
             order, inv = self._perm
             v = self.device_array("vectors")
@@ -416,5 +516,3 @@ class data:
             self.stats["smoothing"] = st
             outp = geo.frame_apply_device(self._gauges_p, out, 1)
             self.vectors = geo.gather_rows_device(outp.contiguous(), inv)
-        else:
-            print('No vectors found. Nothing to smooth.')

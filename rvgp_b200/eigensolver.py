@@ -17,6 +17,7 @@ import numpy as np
 import torch
 
 from ._cabi import get_handle, I64, U64
+from . import _nvtx
 
 _TPC = [None, 0]
 
@@ -306,7 +307,7 @@ class _Dense:
 
 def smallest_eigenpairs(A, k, upper_bound, lower_bound=0.0, tol=1e-12, nex=None, seed=0, max_outer=80,
                         cond_max=1e6, deg0=20, panel=None, stats=None, verbose=False, comm=None,
-                        refine_bound=True, init_fn=None):
+                        refine_bound=True, init_fn=None, hi_override=None, m_exact=None):
     """Smallest k eigenpairs of the symmetric PSD BsrMatrix ``A``.
 
     upper_bound: a rigorous upper bound of the spectrum (2 * max degree for (connection) Laplacians).
@@ -335,10 +336,14 @@ def smallest_eigenpairs(A, k, upper_bound, lower_bound=0.0, tol=1e-12, nex=None,
             # runs keep 64 until measured: RVGP_SHARDED_L_PANEL=128 opts in (8 GPUs: 9 791 steps of 0.09 ms are latency-bound,
             # half as many 128-column steps should cost less; DESIGN.md "next")
             panel = 128
-    if m < Nglob:
+    if m_exact is not None:
+        m = int(min(Nglob, max(k, m_exact)))     # block handed over by krylov.krylov_eigenpairs: exactly its columns
+    elif m < Nglob:
         m = min(Nglob, ((m + panel - 1) // panel) * panel)
     hi = float(upper_bound)
-    if refine_bound and Nglob > 4 * m:
+    if hi_override is not None:
+        hi = float(hi_override)
+    elif refine_bound and Nglob > 4 * m:
         # Gershgorin (2 * max degree) overestimates lambda_max of kNN-graph Laplacians by ~1.5x; the filter degree scales
         # with sqrt(hi), so a 24-step Lanczos bound pays for itself many times over
         hi = min(hi, 1.01 * lanczos_upper_bound(A, comm=comm, h=h))
@@ -381,6 +386,7 @@ def smallest_eigenpairs(A, k, upper_bound, lower_bound=0.0, tol=1e-12, nex=None,
 
     for it in range(max_outer):
         ev0.record()
+        _nvtx.push("eig:filter")
         # ---- polynomial filter: one fused SpMM launch per degree per panel -------------------------
         for p0 in range(0, m, panel):
             p1 = min(m, p0 + panel)
@@ -395,6 +401,8 @@ def smallest_eigenpairs(A, k, upper_bound, lower_bound=0.0, tol=1e-12, nex=None,
             st["filter_launches"] += dg
             st["filter_col_degrees"] += dg * (p1 - p0)
         ev1.record()
+        _nvtx.pop()
+        _nvtx.push("eig:orthonormalise+rayleigh_ritz")
         # ---- orthonormalise: column scaling + Cholesky-QR, then Rayleigh-Ritz with the second
         #      Cholesky folded into the projected problem ---------------------------------------------
         # CholeskyQR passes until one succeeds WITHOUT a diagonal shift (shifted CholeskyQR3: a failed /
@@ -441,6 +449,7 @@ def smallest_eigenpairs(A, k, upper_bound, lower_bound=0.0, tol=1e-12, nex=None,
         st["spmm_launches"] += math.ceil(m / 64)
         res = torch.sqrt(dense.resid_sq(W, V, theta_d)).cpu().numpy()
         ev2.record()
+        _nvtx.pop()
         torch.cuda.synchronize(dev)
         st["t_filter"] += ev0.elapsed_time(ev1) * 1e-3
         st["t_dense"] += ev1.elapsed_time(ev2) * 1e-3
@@ -597,7 +606,7 @@ def _chol_upper_shifted_c(G):
 
 def smallest_eigenpairs_paired(A, k, upper_bound, lower_bound=0.0, tol=1e-12, nex=None, seed=0, max_outer=80,
                                cond_max=1e6, deg0=20, panel=None, stats=None, verbose=False, comm=None,
-                               refine_bound=True, init_fn=None):
+                               refine_bound=True, init_fn=None, hi_override=None, m_exact=None):
     """Smallest k eigenpairs of a d = 2 block matrix ``A`` that commutes with J (all blocks scaled rotations), through its
     complex-Hermitian form.  Same contract as ``smallest_eigenpairs``: returns (evals (k,), evecs (N, k)) with unit-norm
     columns, ascending; columns 2j and 2j+1 are (v_j, J v_j) of the j-th complex eigenpair."""
@@ -620,10 +629,14 @@ def smallest_eigenpairs_paired(A, k, upper_bound, lower_bound=0.0, tol=1e-12, ne
     mc = min(nglob, kc + nexc)
     if panel is None:
         panel = 64 if mc >= 128 else 32
-    if mc < nglob:
+    if m_exact is not None:
+        mc = int(min(nglob, max(kc, m_exact)))
+    elif mc < nglob:
         mc = min(nglob, ((mc + panel - 1) // panel) * panel)
     hi = float(upper_bound)
-    if refine_bound and Nglob > 8 * mc:
+    if hi_override is not None:
+        hi = float(hi_override)
+    elif refine_bound and Nglob > 8 * mc:
         hi = min(hi, 1.01 * lanczos_upper_bound(A, comm=comm, h=h))
     lo_spec = float(lower_bound)
     tol_abs = tol * float(upper_bound)
@@ -687,6 +700,7 @@ def smallest_eigenpairs_paired(A, k, upper_bound, lower_bound=0.0, tol=1e-12, ne
 
     for it in range(max_outer):
         ev0.record()
+        _nvtx.push("eig:filter")
         for p0 in range(0, mc, panel):
             p1 = min(mc, p0 + panel)
             dg = int(deg[p0:p1].max())
@@ -700,6 +714,8 @@ def smallest_eigenpairs_paired(A, k, upper_bound, lower_bound=0.0, tol=1e-12, ne
             st["filter_launches"] += dg
             st["filter_col_degrees"] += dg * (p1 - p0)
         ev1.record()
+        _nvtx.pop()
+        _nvtx.push("eig:orthonormalise+rayleigh_ritz")
         # ---- complex CholeskyQR (shifted CholeskyQR3 on breakdown), then Rayleigh-Ritz ---------------------------------
         for _pass in range(4):
             nrm = dense.coldot(V, V)
@@ -738,6 +754,7 @@ def smallest_eigenpairs_paired(A, k, upper_bound, lower_bound=0.0, tol=1e-12, ne
         st["spmm_launches"] += math.ceil(mc / 64)
         res = torch.sqrt(dense.resid_sq(W, V, theta_d)).cpu().numpy()
         ev2.record()
+        _nvtx.pop()
         torch.cuda.synchronize(dev)
         st["t_filter"] += ev0.elapsed_time(ev1) * 1e-3
         st["t_dense"] += ev1.elapsed_time(ev2) * 1e-3

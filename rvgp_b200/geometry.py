@@ -241,8 +241,9 @@ class ManifoldGraph:
     weighted networkx input).  ``to_networkx()`` materialises the reference's networkx object (geometry.py:112,120-121)
     on demand."""
 
-    def __init__(self, indptr, indices, X=None, knn=None, weights=None):
+    def __init__(self, indptr, indices, X=None, knn=None, weights=None, dense=False):
         self.indptr, self.indices, self.X, self.knn, self.weights = indptr, indices, X, knn, weights
+        self.dense = bool(dense)          # every (i, j) pair stored (typ='affinity')
         self.n = indptr.numel() - 1
         self._nx = None
 
@@ -266,7 +267,10 @@ class ManifoldGraph:
     def to_networkx(self):
         if self._nx is None:
             import networkx as nx
-            G = nx.from_scipy_sparse_array(self.scipy_adjacency())
+            if self.dense:                # nx.from_numpy_array(A) as in geometry.py:118 (zero weights are no edges)
+                G = nx.from_numpy_array(self.weights.reshape(self.n, self.n).cpu().numpy())
+            else:
+                G = nx.from_scipy_sparse_array(self.scipy_adjacency())
             if self.X is not None:
                 Xh = self.X.cpu().numpy() if isinstance(self.X, torch.Tensor) else np.asarray(self.X)
                 nx.set_node_attributes(G, {i: Xh[i] for i in G.nodes}, "pos")
@@ -296,13 +300,29 @@ class ManifoldGraph:
 
 
 def manifold_graph(X, typ="knn", n_neighbors=5, device=None):
-    """Fit graph over a pointset X (geometry.py:100-123).  Only typ='knn' is on the hot path."""
-    if typ != "knn":
-        raise NotImplementedError("typ='%s': only the kNN graph is on the B200 hot path (SURVEY.md 2.1)" % typ)
+    """Fit graph over a pointset X (geometry.py:100-123).
+
+    typ='knn' (the hot path): directed kNN -> + I -> undirected union, unit weights.  Limits of the CUDA kernels:
+    n_neighbors <= 32 and ambient dimension D <= 64 (sklearn, which the reference calls, has no such limits).
+    typ='affinity' (geometry.py:114-118): the DENSE Gaussian-kernel graph exp(-dist^2 / (2 * 0.1^2)) on all pairs incl. the
+    diagonal (weight 1 self loops); n x n weights on the device, n <= 65535.  Its Laplacians come from compute_laplacian;
+    the unit-weight heap-Dijkstra stage (tangent_frames) refuses weighted graphs."""
     Xd = to_device_f64(X, device)
-    knn = knn_device(Xd, n_neighbors)
-    indptr, indices = knn_to_csr_device(knn)
-    return ManifoldGraph(indptr, indices, X=Xd, knn=knn)
+    if typ == "knn":
+        knn = knn_device(Xd, n_neighbors)
+        indptr, indices = knn_to_csr_device(knn)
+        return ManifoldGraph(indptr, indices, X=Xd, knn=knn)
+    if typ == "affinity":
+        n, D = Xd.shape
+        h = get_handle(Xd.device.index)
+        A = torch.empty((n, n), dtype=torch.float64, device=Xd.device)
+        ws = torch.empty(max(1, n), dtype=torch.float64, device=Xd.device)
+        sigma = 0.1                                        # "Control the width of the Gaussian kernel" (geometry.py:116)
+        h.call("rvgp_affinity_f64", Xd, int(n), int(D), float(sigma), A, ws)
+        indptr = (torch.arange(n + 1, device=Xd.device, dtype=torch.int64) * n).to(torch.int32)
+        indices = torch.arange(n, device=Xd.device, dtype=torch.int32).repeat(n)
+        return ManifoldGraph(indptr, indices, X=Xd, weights=A.reshape(-1), dense=True)
+    raise ValueError("manifold_graph: typ must be 'knn' or 'affinity', got %r" % (typ,))   # the reference hits a NameError here
 
 
 def manifold_dimension(Sigma, frac_explained=0.9):

@@ -1,0 +1,431 @@
+"""Filtered block Lanczos with thick restart: the fast path of the smallest-k eigensolver for large problems.
+
+Replaces ``scipy.sparse.linalg.eigsh(A, k, which="SM")`` = ARPACK (reference RVGP/geometry.py:66-80) together with
+``eigensolver.smallest_eigenpairs`` (Chebyshev-filtered SUBSPACE iteration, ChFSI), which remains the general solver and
+the final Rayleigh-Ritz / polishing stage of this one.
+
+Why.  ChFSI applies a degree ~1000 polynomial to ALL m = k + 20 % columns (C4: 627 840 column-degrees for the scalar
+Laplacian, 77 % of the whole pipeline).  A block KRYLOV space needs the same total polynomial degree, but only on b = 64
+columns: span{Q, BQ, B^2 Q, ...} contains every intermediate power, and the Rayleigh-Ritz over the whole space does what
+the extra columns did.  Measured on the C2 problem (n = 35 000, k = 200, CPU prototype): 20 168 column-degrees against
+71 424, same eigenvalues (8e-15) and residuals.
+
+Method.  B = rho_d(A) is the scaled Chebyshev filter of degree d that ChFSI uses (one fused SpMM launch per degree,
+``cheb_filter``), with a FIXED damped interval [cut, hi]; cut sits above the wanted eigenvalues (lambda_{~1.5 k}).  Block
+Lanczos on B with full (two-pass classical Gram-Schmidt) orthogonalisation:
+    W = B Q_j ;  C = V^T W ;  W -= V C  (twice) ;  W = Q_{j+1} R (CholeskyQR2) ;  T[:, j] = C,  T[j+1, j] = R
+The projected matrix T = V^T B V costs nothing extra (it IS the orthogonalisation coefficients).  When the basis is full:
+thick restart (keep the best Ritz vectors of T, the coupling row R Y_last, and the newest block).  Convergence is
+predicted from the Lanczos residual estimates ||R Y_last[:, i]|| and then VERIFIED with true residuals ||A x - theta x||;
+the final Ritz vectors go through one ChFSI Rayleigh-Ritz in A-space, which also polishes in the (rare) case that a pair
+is still above tolerance.  The stopping rule is therefore exactly the ChFSI one: true residuals <= tol * upper_bound.
+
+``FieldOps`` hides the scalar field: real symmetric operators, and the complex-Hermitian form of the d = 2 connection
+Laplacian (paired mode, eigensolver.py) where a column of the (2n x b) real block IS one complex vector:
+V^H W = V^T W - i V^T (J W),  V C = V Re C + J (V Im C).
+
+All device math is librvgp_b200.so (fused SpMM filter, FP64 dgemm); the host sees only b x b and m x m matrices.
+"""
+import math
+import time
+
+import numpy as np
+import torch
+
+from ._cabi import get_handle, I64, U64
+from . import _nvtx
+from .eigensolver import (_lapack_ctx, _tri_inv_upper, lanczos_upper_bound, smallest_eigenpairs, smallest_eigenpairs_paired,
+                          BsrMatrix)
+
+
+class FieldOps:
+    """Block operations of the Krylov iteration on (N x cap) device bases; ``cplx`` selects the paired (complex) algebra."""
+
+    def __init__(self, h, N, cap, b, dev, comm, cplx):
+        self.h, self.N, self.cap, self.b, self.dev, self.comm, self.cplx = h, N, cap, b, dev, comm, cplx
+        self.Cd = torch.empty((cap, b), dtype=torch.float64, device=dev)          # Gram output / coefficient upload (real part)
+        self.Ci = torch.empty((cap, b), dtype=torch.float64, device=dev) if cplx else None
+        self.split = max(1, min(64, (4 * h.sm_count) // max(1, math.ceil(cap / 128)), N // 2048 if N >= 4096 else 1))
+        self.ws = torch.empty(self.split * cap * b, dtype=torch.float64, device=dev)
+        self.tmp = torch.empty((N, b), dtype=torch.float64, device=dev)           # J W / V Im(C) scratch
+        self.flops = 0.0
+
+    # ---- primitives --------------------------------------------------------------------------------------------
+    def _gram_real(self, Vc, W, out):
+        cur, nb = Vc.shape[1], W.shape[1]
+        o = out[:cur, :nb]
+        self.h.call("rvgp_dgemm_f64", int(cur), int(nb), I64(self.N), 1.0, Vc, I64(Vc.stride(0)), 0, W, I64(W.stride(0)), 0, None,
+                    o, I64(out.stride(0)), int(self.split), self.ws)
+        self.flops += 2.0 * self.N * cur * nb
+        return o
+
+    def _rot(self, X, out):
+        self.h.call("rvgp_rot90_nodes_f64", I64(self.N // 2), int(X.shape[1]), X, I64(X.stride(0)), out, I64(out.stride(0)))
+        return out
+
+    def _acc(self, Vc, Cdev, W, alpha):
+        """W += alpha * Vc @ Cdev."""
+        cur, nb = Vc.shape[1], W.shape[1]
+        self.h.call("rvgp_dgemm_acc_f64", int(self.N), int(nb), I64(cur), float(alpha), Vc, I64(Vc.stride(0)), 1, Cdev,
+                    I64(Cdev.stride(0)), 0, 1.0, W, I64(W.stride(0)))
+        self.flops += 2.0 * self.N * cur * nb
+
+    # ---- block operations -----------------------------------------------------------------------------------------
+    def project_out(self, Vc, W):
+        """One classical Gram-Schmidt pass: C = Vc^H W (all-reduced over the ranks), W -= Vc C.  Returns C on the host."""
+        cur, nb = Vc.shape[1], W.shape[1]
+        Cr = self._gram_real(Vc, W, self.Cd)
+        if self.cplx:
+            JW = self._rot(W, self.tmp[:, :nb])
+            Ci = self._gram_real(Vc, JW, self.Ci)
+            if self.comm is not None:
+                self.comm.allreduce_(Cr); self.comm.allreduce_(Ci)
+            Ci.neg_()                                        # Im C = -Vc^T (J W)
+            self._acc(Vc, Cr, W, -1.0)                       # W -= Vc Re C
+            t = self.tmp[:, :nb]
+            self.h.call("rvgp_dgemm_f64", int(self.N), int(nb), I64(cur), 1.0, Vc, I64(Vc.stride(0)), 1, Ci, I64(self.Ci.stride(0)),
+                        0, None, t, I64(t.stride(0)), 1, None)
+            self.flops += 2.0 * self.N * cur * nb
+            self._sub_rot(W, t)                              # W -= J (Vc Im C)
+            return Cr.cpu().numpy() + 1j * Ci.cpu().numpy()
+        if self.comm is not None:
+            self.comm.allreduce_(Cr)
+        self._acc(Vc, Cr, W, -1.0)
+        return Cr.cpu().numpy().copy()
+
+    def _sub_rot(self, W, t):
+        """W -= J t for (N x nb) blocks (J = per-node quarter turn)."""
+        nb = W.shape[1]
+        if not hasattr(self, "_jt"):
+            self._jt = torch.empty((self.N, self.b), dtype=torch.float64, device=self.dev)
+        jt = self._rot(t, self._jt[:, :nb])
+        self.h.call("rvgp_axpy_f64", I64(self.N), int(nb), -1.0, jt, I64(jt.stride(0)), W, I64(W.stride(0)))
+
+    def gram_self(self, W):
+        """W^H W on the host (Hermitian / symmetric)."""
+        nb = W.shape[1]
+        Gr = self._gram_real(W, W, self.Cd)
+        if self.cplx:
+            JW = self._rot(W, self.tmp[:, :nb])
+            Gi = self._gram_real(W, JW, self.Ci)
+            if self.comm is not None:
+                self.comm.allreduce_(Gr); self.comm.allreduce_(Gi)
+            G = Gr.cpu().numpy() - 1j * Gi.cpu().numpy()
+            return 0.5 * (G + G.conj().T)
+        if self.comm is not None:
+            self.comm.allreduce_(Gr)
+        G = Gr.cpu().numpy()
+        return 0.5 * (G + G.T)
+
+    def right_multiply(self, Vc, M, out):
+        """out (N x p) = Vc @ M for a host matrix M (cur x p), real or complex."""
+        cur, p = M.shape
+        Md = torch.from_numpy(np.ascontiguousarray(M.real if self.cplx else M, dtype=np.float64)).to(self.dev)
+        self.h.call("rvgp_dgemm_f64", int(self.N), int(p), I64(cur), 1.0, Vc, I64(Vc.stride(0)), 1, Md, I64(Md.stride(0)), 0, None,
+                    out, I64(out.stride(0)), 1, None)
+        self.flops += 2.0 * self.N * cur * p
+        if self.cplx:
+            Mi = torch.from_numpy(np.ascontiguousarray(M.imag, dtype=np.float64)).to(self.dev)
+            for c0 in range(0, p, self.b):                   # out += J (Vc Im M), one scratch panel at a time
+                c1 = min(p, c0 + self.b)
+                t = self.tmp[:, :c1 - c0]
+                self.h.call("rvgp_dgemm_f64", int(self.N), int(c1 - c0), I64(cur), -1.0, Vc, I64(Vc.stride(0)), 1, Mi[:, c0:c1],
+                            I64(Mi.stride(0)), 0, None, t, I64(t.stride(0)), 1, None)
+                self._sub_rot(out[:, c0:c1], t)              # out -= J (-(Vc Im M)) = out + J (Vc Im M)
+                self.flops += 2.0 * self.N * cur * (c1 - c0)
+        return out
+
+    def cholqr2(self, W, out, st):
+        """out = orthonormal basis of span(W) (CholeskyQR2; shifted first pass when W is numerically rank deficient).
+        Returns R (host, b x b, upper) with W = out R."""
+        nb = W.shape[1]
+        Rtot = np.eye(nb, dtype=np.complex128 if self.cplx else np.float64)
+        src = W
+        for _pass in range(3):
+            G = self.gram_self(src)
+            t0 = time.perf_counter()
+            with _lapack_ctx():
+                shifted = False
+                try:
+                    R = np.linalg.cholesky(G).conj().T
+                except np.linalg.LinAlgError:
+                    shifted = True
+                    shift = 1e-13 * nb * max(float(np.abs(np.diag(G)).max()), 1e-300)
+                    while True:
+                        try:
+                            R = np.linalg.cholesky(G + shift * np.eye(nb)).conj().T
+                            break
+                        except np.linalg.LinAlgError:
+                            shift *= 100.0
+                Rinv = _tri_inv_upper(R)
+            st["t_host"] += time.perf_counter() - t0
+            dst = out if src is not out else self._swap(out)
+            self.right_multiply(src, Rinv, dst)
+            if dst is not out:
+                out.copy_(dst)
+            src = out
+            Rtot = R @ Rtot
+            if _pass >= 1 and not shifted:
+                break
+        return Rtot
+
+    def _swap(self, like):
+        if not hasattr(self, "_sw"):
+            self._sw = torch.empty((self.N, self.b), dtype=torch.float64, device=self.dev)
+        return self._sw[:, :like.shape[1]]
+
+
+def _filter_degree(cut, lam_k, hi, lo, nats):
+    e, c = 0.5 * (hi - cut), 0.5 * (hi + cut)
+    gk = math.acosh(max((c - lam_k) / e, 1.0 + 1e-12))
+    g0 = math.acosh(max((c - lo) / e, 1.0 + 1e-12))
+    d = int(math.ceil(nats / gk))
+    d = min(d, int(math.log(1e13) / g0))            # keep rho(unwanted) / rho(lo) above the rounding floor
+    return max(4, min(600, d)), gk, g0
+
+
+def _rho_inverse(theta, cut, hi, lo, d):
+    """lambda with rho_d(lambda) = theta for the scaled filter (rho(lo) = 1, |rho| <= 1 / cosh(d g0) on [cut, hi])."""
+    e, c = 0.5 * (hi - cut), 0.5 * (hi + cut)
+    g0 = math.acosh(max((c - lo) / e, 1.0 + 1e-12))
+    y = max(float(theta) * math.cosh(d * g0), 1.0)
+    return c - e * math.cosh(math.acosh(y) / d)
+
+
+def krylov_eigenpairs(A, k, upper_bound, cut, lam_k, paired=False, tol=1e-12, block=64, nats=3.5, seed=0, stats=None, comm=None,
+                      refine_bound=True, lower_bound=0.0, cap_cols=None, max_blocks=400, init_fn=None, verbose=False,
+                      _depth=0, _hi=None):
+    """Smallest k eigenpairs of the symmetric PSD operator ``A`` (BsrMatrix / ShardedBsr) by filtered block Lanczos.
+
+    cut    lower end of the damped interval: an estimate of lambda_J with J ~ 1.5 k (too high only costs time; it must not be
+           below lambda_k).  lam_k: estimate of lambda_k (sets the filter degree).  paired: complex-Hermitian form of a d = 2
+           operator whose blocks are all scaled rotations (k counts REAL eigenpairs, as in smallest_eigenpairs_paired).
+    Returns (evals (k,), evecs (N, k)) exactly like eigensolver.smallest_eigenpairs[_paired]; ``stats`` gets the same keys.
+    """
+    dev = A.indptr.device
+    h = get_handle(dev.index)
+    N = A.nrows
+    Nglob = N
+    if comm is not None and comm.world > 1:
+        t = torch.tensor([N], dtype=torch.int64, device=dev)
+        comm.allreduce_(t)
+        Nglob = int(t.item())
+    else:
+        comm = None
+    b = int(block)
+    kw = (k + 1) // 2 if paired else k                   # wanted pairs in the field the iteration works in
+    nfield = Nglob // 2 if paired else Nglob
+    hi = float(upper_bound)
+    if _hi is not None:
+        hi = _hi
+    elif refine_bound:
+        hi = min(hi, 1.01 * lanczos_upper_bound(A, comm=comm, h=h))
+    lo = float(lower_bound)
+    tol_abs = tol * float(upper_bound)
+    cut = float(min(max(cut, 1.02 * lam_k), 0.5 * hi))
+    d, gk, g0 = _filter_degree(cut, lam_k, hi, lo, nats)
+    # capacity: start-up (the space needs >= kw dimensions) + converging blocks + spare, then thick restarts
+    f = math.acosh(2.0 * math.cosh(d * gk) - 1.0)
+    nblk_est = math.ceil(kw / b) + math.ceil(40.0 / f) + 2
+    keep = kw + 2 * b                                    # Ritz vectors kept at a thick restart
+    cap = (nblk_est + 3) * b if cap_cols is None else int(cap_cols)
+    cap = max(cap, keep + 4 * b)
+    cap = min(cap, (nfield // b) * b)
+    st = stats if stats is not None else {}
+    panel = b
+    st.update(dict(N=N, k=k, m=cap, panel=panel, spmm_launches=0, filter_launches=0, filter_col_degrees=0, outer=0, t_filter=0.0,
+                   t_dense=0.0, t_host=0.0, spmm_bytes_fused=int(A.spmm_bytes(panel, fused=True)),
+                   spmm_bytes_plain=int(A.spmm_bytes(panel, fused=False)), d=A.d, world=(comm.world if comm else 1), hi=hi,
+                   hi_gershgorin=float(upper_bound), solver="filtered block Lanczos", paired=bool(paired), cut=cut, lam_k_est=float(lam_k),
+                   degree=d, blocks=0, restarts=0, checks=0, cap=cap))
+
+    V = torch.empty((N, cap), dtype=torch.float64, device=dev)
+    w0 = torch.empty((N, b), dtype=torch.float64, device=dev)
+    w1 = torch.empty((N, b), dtype=torch.float64, device=dev)
+    w2 = torch.empty((N, b), dtype=torch.float64, device=dev) if (isinstance(A, BsrMatrix) and A.mma is not None and A.d == 2) else None
+    Wb = torch.empty((N, b), dtype=torch.float64, device=dev)             # the block being filtered (contiguous panel)
+    st["spmm_kernel"] = "mma_native" if w2 is not None else "gather"
+    ops = FieldOps(h, N, cap, b, dev, comm, paired)
+    cdt = np.complex128 if paired else np.float64
+    T = np.zeros((cap, cap), dtype=cdt)
+
+    ev0, ev1, ev2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+
+    # ---- first block --------------------------------------------------------------------------------------------
+    h.call("rvgp_fill_uniform_f64", I64(N), int(b), Wb, I64(Wb.stride(0)), U64(seed), I64(0), I64(A.row_offset))
+    if init_fn is not None:
+        init_fn(Wb)
+    ops.cholqr2(Wb, V[:, :b], st)
+    cur = b
+    converged = False
+    X = None
+    theta_B = None
+    retry_cut = None
+    rho_cut = 1.0 / math.cosh(d * g0)                    # level of the damped part of the spectrum under B
+    next_check = math.ceil(kw / b) + max(2, math.ceil(22.0 / f))
+
+    def ritz(m):
+        """Ritz pairs of T[:m, :m], largest first (largest of B = smallest of A), and Lanczos residual estimates."""
+        t0 = time.perf_counter()
+        with _lapack_ctx():
+            th, Y = np.linalg.eigh(T[:m, :m])
+        st["t_host"] += time.perf_counter() - t0
+        th, Y = th[::-1], Y[:, ::-1]
+        Rc = T[m:m + b, m - b:m]
+        resB = np.linalg.norm(Rc @ Y[m - b:m, :], axis=0)
+        return th, Y, resB
+
+    for blk in range(max_blocks):
+        j0 = cur - b
+        ev0.record()
+        _nvtx.push("eig:filter")
+        Wb.copy_(V[:, j0:cur])
+        if w2 is not None:
+            A.cheb_filter(Wb, w0, w1, b, d, lo, cut, hi, h=h, w2=w2)
+        else:
+            A.cheb_filter(Wb, w0, w1, b, d, lo, cut, hi, h=h)
+        st["spmm_launches"] += d
+        st["filter_launches"] += d
+        st["filter_col_degrees"] += d * b
+        ev1.record()
+        _nvtx.pop()
+        _nvtx.push("eig:orthogonalise")
+        Vc = V[:, :cur]
+        C = ops.project_out(Vc, Wb)
+        C = C + ops.project_out(Vc, Wb)
+        T[:cur, j0:cur] = C
+        T[j0:cur, :cur] = C.conj().T
+        T[j0:cur, j0:cur] = 0.5 * (C[j0:cur] + C[j0:cur].conj().T)
+        R = ops.cholqr2(Wb, V[:, cur:cur + b], st)
+        T[cur:cur + b, j0:cur] = R
+        T[j0:cur, cur:cur + b] = R.conj().T
+        cur += b
+        st["blocks"] += 1
+        ev2.record()
+        _nvtx.pop()
+        torch.cuda.synchronize(dev)
+        st["t_filter"] += ev0.elapsed_time(ev1) * 1e-3
+        st["t_dense"] += ev1.elapsed_time(ev2) * 1e-3
+
+        full = cur + b > cap
+        if st["blocks"] >= next_check or full:
+            m = cur - b
+            if m < kw + 1:
+                next_check = st["blocks"] + 1
+                if not full:
+                    continue
+            th, Y, resB = ritz(m)
+            st["checks"] += 1
+            nw = min(kw, m)
+            # Lanczos estimate of the A-residual: an error direction in the damped region is seen by B with weight theta_i,
+            # by A with weight <= hi
+            estA = resB[:nw] * hi / np.maximum(np.abs(th[:nw]), 1e-300)
+            if verbose:
+                print("  [krylov] blocks %d dim %d  est max %.3e (tol %.2e)  theta_B[kw-1] %.3e" % (st["blocks"], m, estA.max(), tol_abs, th[nw - 1]))
+            if nw == kw and m >= kw + b and th[kw - 1] < 4.0 * rho_cut and _depth < 2:
+                # the kw-th Ritz value of B sits at the level of the DAMPED interval: the cut estimate was below lambda_kw and the
+                # top of the wanted spectrum is being filtered away.  Start again with a cut placed from what the run has learnt.
+                known = [_rho_inverse(t, cut, hi, lo, d) for t in th[:kw] if t > 8.0 * rho_cut]
+                lam_seen = known[-1] if known else cut
+                frac = max(len(known), 1) / float(kw)
+                retry_cut = max(1.6 * cut, 1.6 * lam_seen / max(frac, 0.25))
+                st["cut_retry"] = dict(old_cut=cut, new_cut=retry_cut, resolved=len(known))
+                break
+            if nw == kw and estA.max() <= 4.0 * tol_abs:
+                # verify on the hardest wanted pairs with TRUE residuals before handing over
+                t_ev = time.perf_counter()
+                hard = np.argsort(-estA)[:min(16, kw)]
+                hard.sort()
+                Xh = torch.empty((N, len(hard)), dtype=torch.float64, device=dev)
+                ops.right_multiply(V[:, :m], Y[:, hard], Xh)
+                res_h = _true_residuals(A, Xh, ops, h, comm)
+                if verbose:
+                    print("  [krylov]   true residual of the hardest pairs: %.3e" % res_h.max())
+                if res_h.max() <= tol_abs:
+                    converged = True
+                    pk = min(m, ((kw + 8 + 15) // 16) * 16)
+                    X = torch.empty((N, pk), dtype=torch.float64, device=dev)
+                    ops.right_multiply(V[:, :m], Y[:, :pk], X)
+                    theta_B = th[:pk]
+                    break
+                next_check = st["blocks"] + max(1, int(math.ceil(math.log(max(res_h.max() / tol_abs, 2.0)) / f)))
+            else:
+                need = math.log(max(estA.max() / (2.0 * tol_abs), 2.0)) / f if nw == kw else 2
+                next_check = st["blocks"] + max(1, min(8, int(math.ceil(need))))
+            if full:
+                # ---- thick restart: keep the `keep` best Ritz vectors of T[:m,:m], their coupling to the newest block, and
+                #      the newest block itself (a valid Krylov-Schur decomposition of B)
+                p = min(keep, m - b)
+                Xk = torch.empty((N, p), dtype=torch.float64, device=dev)
+                ops.right_multiply(V[:, :m], Y[:, :p], Xk)
+                V[:, p:p + b].copy_(V[:, m:cur].clone())
+                V[:, :p].copy_(Xk)
+                del Xk
+                Cpl = T[m:cur, m - b:m] @ Y[m - b:m, :p]
+                Tn = np.zeros_like(T)
+                Tn[:p, :p] = np.diag(th[:p])
+                Tn[p:p + b, :p] = Cpl
+                Tn[:p, p:p + b] = Cpl.conj().T
+                T = Tn
+                cur = p + b
+                st["restarts"] += 1
+    st["outer"] = st["blocks"]
+    st["dense_tflop"] = ops.flops / 1e12
+    if retry_cut is not None:
+        del V, w0, w1, w2, Wb, ops
+        prev = dict(st)
+        out = krylov_eigenpairs(A, k, upper_bound, retry_cut, retry_cut / 1.5, paired=paired, tol=tol, block=block, nats=nats,
+                                seed=seed, stats=st, comm=comm, lower_bound=lower_bound, cap_cols=cap_cols, max_blocks=max_blocks,
+                                init_fn=init_fn, verbose=verbose, _depth=_depth + 1, _hi=hi)
+        for key in ("spmm_launches", "filter_launches", "filter_col_degrees", "t_filter", "t_dense", "t_host", "blocks", "checks"):
+            st[key] += prev.get(key, 0)
+        st["cut_retries"] = _depth + 1
+        return out
+    if X is None:
+        # not converged within max_blocks: hand the best Ritz vectors to ChFSI, which iterates to the same stopping rule
+        m = cur - b
+        th, Y, _ = ritz(m)
+        pk = min(m, ((kw + 8 + 15) // 16) * 16)
+        X = torch.empty((N, pk), dtype=torch.float64, device=dev)
+        ops.right_multiply(V[:, :m], Y[:, :pk], X)
+    del V, w0, w1, w2, Wb, ops
+    st["krylov_converged"] = converged
+
+    # ---- final Rayleigh-Ritz in A-space (and polishing, should a pair still be above tolerance): the ChFSI code path with
+    #      the Krylov Ritz vectors as its start block and no filter in the first sweep
+    pk = X.shape[1]
+    st2 = {}
+    Xref = [X]
+
+    def start(Vdst):
+        Vdst[:, :pk].copy_(Xref[0])
+        Xref[0] = None
+
+    fin = smallest_eigenpairs_paired if paired else smallest_eigenpairs
+    X = None
+    evals, evecs = fin(A, k, upper_bound, lower_bound=lower_bound, tol=tol, seed=seed + 1, deg0=0, panel=b, stats=st2, comm=comm,
+                       refine_bound=False, init_fn=start, hi_override=hi, m_exact=pk)
+    for key in ("spmm_launches", "filter_launches", "filter_col_degrees", "t_filter", "t_dense", "t_host"):
+        st[key] += st2.get(key, 0)
+    st["final_rr_outer"] = st2.get("outer")
+    st["m_final"] = st2.get("m")
+    st["residual_max"], st["converged"], st["tol_abs"] = st2["residual_max"], st2["converged"], st2["tol_abs"]
+    st["cholqr_passes"] = st2.get("cholqr_passes", 0)
+    return evals, evecs
+
+
+def _true_residuals(A, X, ops, h, comm):
+    """||A x - (x^H A x) x|| per column of the orthonormal block X (host array)."""
+    N, p = X.shape
+    AX = A.matmat(X.contiguous(), h=h)
+    dev = X.device
+    ws = torch.empty(max(1, h.query("rvgp_coldot_workspace_bytes", I64(N), int(p)) // 8), dtype=torch.float64, device=dev)
+    lam = torch.empty(p, dtype=torch.float64, device=dev)
+    h.call("rvgp_coldot_f64", I64(N), int(p), X, I64(X.stride(0)), AX, I64(AX.stride(0)), lam, ws)
+    if comm is not None:
+        comm.allreduce_(lam)
+    r2 = torch.empty(p, dtype=torch.float64, device=dev)
+    h.call("rvgp_resid_sq_f64", I64(N), int(p), AX, I64(AX.stride(0)), X, I64(X.stride(0)), lam, r2, ws)
+    if comm is not None:
+        comm.allreduce_(r2)
+    return torch.sqrt(r2).cpu().numpy()

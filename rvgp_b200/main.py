@@ -21,6 +21,7 @@ from sklearn.model_selection import train_test_split
 from . import params as P
 from .geometry import furthest_point_sampling, gather_rows_device, to_device_f64  # noqa: F401
 from ._cabi import RvgpError
+from . import _nvtx
 from .gp import DeviceGPR
 from .gp_general import DenseGPR, DeviceSGPR
 from .kernels import ManifoldKernel, RBF
@@ -135,7 +136,8 @@ class _Model:
             nodes = _as_node_indices(test_ind, data.n)
             test_x = _node_rows_device(data, nodes)
             n_out = len(nodes)
-        f_pred_mean, f_pred_std = self.predict_f(test_x)
+        with _nvtx.stage('transform:predict_f'):
+            f_pred_mean, f_pred_std = self.predict_f(test_x)
         if as_device:       # bench.py's device-resident leg: keep the result in HBM
             return f_pred_mean.tensor.reshape(n_out, -1), f_pred_std.tensor.reshape(n_out, -1)
         f_pred_mean = f_pred_mean.numpy().reshape(n_out, -1)
@@ -311,7 +313,8 @@ def train_gp(data,
         kernel.lengthscales.assign(kernel_lengthscale)
         P.set_trainable(kernel.lengthscales, False)
 
-    GP = optimize_model_with_scipy(GP, epochs)
+    with _nvtx.stage('fit:optimise'):
+        GP = optimize_model_with_scipy(GP, epochs)
 
     # test
     out_pred, _ = GP.predict_f(in_test)

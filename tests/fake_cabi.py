@@ -194,3 +194,106 @@ def install(monkeypatch):
         if hasattr(mod, "to_device_f64"):
             monkeypatch.setattr(mod, "to_device_f64", fake_to_device)
     return fh
+
+
+# ---- eigensolver entry points (tests/test_krylov_host.py) -----------------------------------------------------------
+def _fake_fill_uniform(self, nrows, ncols, A, lda, seed, col_offset, row_offset):
+    g = np.random.default_rng([int(seed), int(col_offset), int(row_offset)])
+    _mat(A, nrows, ncols, lda).copy_(torch.from_numpy(g.uniform(-1.0, 1.0, (int(nrows), int(ncols)))))
+    return 0
+
+
+def _fake_rot90(self, nnodes, ncols, V, ldv, out, ldo):
+    Vm, Om = _mat(V, 2 * nnodes, ncols, ldv), _mat(out, 2 * nnodes, ncols, ldo)
+    Om[0::2] = -Vm[1::2]
+    Om[1::2] = Vm[0::2]
+    return 0
+
+
+def _fake_resid_sq(self, nrows, ncols, W, ldw, V, ldv, theta, out, ws):
+    Wm = _mat(W, nrows, ncols, ldw)
+    Vm = _mat(V, nrows, ncols, ldv) if V is not None else torch.ones_like(Wm)
+    out[:ncols].copy_(((Wm - Vm * theta[:ncols][None, :]) ** 2).sum(0))
+    return 0
+
+
+def _fake_dgemm_lower(self, m, n, k, alpha, A, lda, a_kmajor, B, ldb, b_kmajor, C, ldc, split_k, ws):
+    Am = _op(A, m, k, lda, a_kmajor == 1)
+    Bm = _op(B, k, n, ldb, b_kmajor == 0)
+    full = alpha * (Am @ Bm)
+    # only tiles touching the lower triangle are defined: poison the strict upper part beyond the diagonal tiles
+    _mat(C, m, n, ldc).copy_(torch.tril(full) + torch.triu(torch.full_like(full, float("nan")), 1))
+    return 0
+
+
+FakeHandle.rvgp_fill_uniform_f64 = _fake_fill_uniform
+FakeHandle.rvgp_rot90_nodes_f64 = _fake_rot90
+FakeHandle.rvgp_resid_sq_f64 = _fake_resid_sq
+FakeHandle.rvgp_dgemm_lower_f64 = _fake_dgemm_lower
+
+
+class FakeBsr:
+    """Duck-type of eigensolver.BsrMatrix over a SciPy matrix: the operator side of the C ABI (fused SpMM filter, products)."""
+    mma = None
+    row_offset = 0
+    vals = 1
+
+    def __init__(self, M, d=1):
+        import scipy.sparse as sp
+        self.M = sp.csr_matrix(M)
+        self.d = int(d)
+        self.nrows = self.M.shape[0]
+        self.nbrows = self.nrows // self.d
+        self.indptr = torch.zeros(1, dtype=torch.int32)          # only its .device is read
+        self.col_degrees = 0
+
+    def spmm_bytes(self, ncols, fused=False):
+        return int(self.M.nnz * 12 + 8 * self.nrows * ncols * (3 if fused else 2))
+
+    def matmat(self, X, out=None, h=None):
+        Y = torch.from_numpy(self.M @ X.numpy())
+        if out is None:
+            return Y
+        out.copy_(Y)
+        return out
+
+    def cheb_filter(self, Vp, w0, w1, ncols, degree, lo_spec, lo_cut, hi, h=None, w2=None):
+        """The scaled three-term recurrence of rvgp_cheb_filter_f64 (csrc/spmm.cu), in place on the panel Vp."""
+        if degree <= 0:
+            return
+        A = self.M
+        V = Vp.numpy().copy()
+        e, c = 0.5 * (hi - lo_cut), 0.5 * (hi + lo_cut)
+        s1 = e / (lo_spec - c)
+        tau, sig = 2.0 / s1, s1
+        Y = (A @ V - c * V) * (s1 / e)
+        X = V
+        for _ in range(2, degree + 1):
+            sn = 1.0 / (tau - sig)
+            Y, X = (A @ Y - c * Y) * (2.0 * sn / e) - sig * sn * X, Y
+            sig = sn
+        Vp.copy_(torch.from_numpy(Y))
+        self.col_degrees += degree * ncols
+
+
+def install_eigensolver(monkeypatch):
+    """CPU emulation for eigensolver.py / krylov.py: fake handle, and no-op CUDA events / synchronisation."""
+    import importlib
+    fh = FakeHandle()
+    for modname in ("rvgp_b200.eigensolver", "rvgp_b200.krylov"):
+        mod = importlib.import_module(modname)
+        monkeypatch.setattr(mod, "get_handle", lambda device=None: fh)
+
+    class _Ev:
+        def __init__(self, enable_timing=False):
+            pass
+
+        def record(self):
+            pass
+
+        def elapsed_time(self, other):
+            return 0.0
+
+    monkeypatch.setattr(torch.cuda, "Event", _Ev)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda device=None: None)
+    return fh

@@ -69,14 +69,20 @@ def test_oracle_front_end_matches_c2_golden():
 
 
 @pytest.mark.gpu
-def test_cuda_data_object_matches_c2_golden():
+@pytest.mark.parametrize("solver", ["auto", "krylov"])
+def test_cuda_data_object_matches_c2_golden(solver, monkeypatch):
+    """solver = "krylov" forces the filtered block Lanczos eigensolver (krylov.py; the default only from n = 100 000 on), so
+    that BOTH eigensolvers are pinned to the reference's ARPACK output at the largest size the reference can run."""
     import RVGP
     import torch
+    monkeypatch.setenv("RVGP_EIGSOLVER", solver)
     g = _golden()
     n, k, nb = int(g["n"]), int(g["k"]), int(g["nb"])
     X = make_cloud("torus", n, 0)
     d = RVGP.create_data_object(X, n_neighbors=nb, n_eigenpairs=k, verbose=False)
     assert d.dim_man == int(g["dim_man"])
+    assert ("Lanczos" in str(d.stats["eig_L"].get("solver"))) == (solver == "krylov")
+    assert ("Lanczos" in str(d.stats["eig_Lc"].get("solver"))) == (solver == "krylov")
     gr = d._graph
     assert _sha(np.sort(gr.knn.cpu().numpy(), axis=1).astype(np.int32)) == str(g["knn_sha"])            # bit-exact sets
     assert _sha(gr.indices.cpu().numpy().astype(np.int32)) == str(g["L_indices_sha"])

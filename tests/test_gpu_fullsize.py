@@ -87,4 +87,6 @@ def test_properties_c2_size():
 
 
 def test_properties_200k():
-    _props(200000, 100)
+    d = _props(200000, 128)
+    # large problems take the filtered block Lanczos path (krylov.py); the invariants above are solver-independent
+    assert "Lanczos" in str(d.stats["eig_L"].get("solver")) and "Lanczos" in str(d.stats["eig_Lc"].get("solver"))

@@ -26,14 +26,24 @@ def main():
     # timing at C2 scale
     from tests.workloads import make_cloud
     X = make_cloud("torus", int(os.environ.get("DIST_N", "200000")), 0)
+    big = {}
     for shard, peer in ((True, "1"), (True, "0"), (False, "1")):
         os.environ["RVGP_PEER_HALO"] = peer
         torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
         d = data(X, n_eigenpairs=200, verbose=False, shard=shard)
         torch.cuda.synchronize(); dist.barrier()
+        big[(shard, peer)] = (d.evals_L.copy(), d.evals_Lc.copy())
         if rank == 0:
             print("n=%d k=200 shard=%s peer_halo=%s world=%d: %.2f s  stages %s  eig_Lc %s halo %s" % (len(X), shard, peer, world, time.perf_counter() - t0,
-                  {a: round(b, 2) for a, b in d.timings.items()}, {a: d.stats["eig_Lc"][a] for a in ("outer", "filter_launches", "t_filter", "t_dense", "spmm_kernel")}, d.stats.get("halo")))
+                  {a: round(b, 2) for a, b in d.timings.items()}, {a: d.stats["eig_Lc"].get(a) for a in ("solver", "outer", "filter_launches", "t_filter", "t_dense", "t_host", "spmm_kernel")}, d.stats.get("halo")))
+        del d
+    # large problems run the filtered block Lanczos solver (krylov.py): sharded (both halo paths) == single GPU
+    for key in ((True, "1"), (True, "0")):
+        dL = np.abs(big[key][0] - big[(False, "1")][0]).max()
+        dLc = np.abs(big[key][1] - big[(False, "1")][1]).max() / big[(False, "1")][1].max()
+        if rank == 0:
+            print("n=%d sharded(peer=%s) vs single: evals_L abs %.2e  evals_Lc rel %.2e" % (len(X), key[1], dL, dLc))
+        ok = ok and dL < 1e-9 and dLc < 1e-9
     os.environ["RVGP_PEER_HALO"] = "1"
     if rank == 0:
         print("DIST_CHECK", "PASS" if ok else "FAIL")

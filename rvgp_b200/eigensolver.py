@@ -19,28 +19,32 @@ import torch
 from ._cabi import get_handle, I64, U64
 from . import _nvtx
 
-_TPC = [None, 0]
+_TPC = [None, 0, 0]
 
 
-def _lapack_ctx():
+def _lapack_ctx(big=False):
     """Context for the host LAPACK sections (the m x m projected problems): a FEW BLAS threads.  Measured on the B200 box
     (16 host cores, tools/host_lapack_probe.py, profiles/r01d_host_lapack.txt): one outer iteration's Cholesky + triangular
     inverse + projection + eigh of a 640 x 640 problem takes 205 ms with OpenBLAS's default 16 threads, 51 ms with 4 and
     86 ms with 1 (torchrun's OMP_NUM_THREADS=1).  Threads per rank: host cores / (4 * ranks on the node), clamped to [1, 4];
-    RVGP_HOST_THREADS overrides."""
+    ``big`` (the >= 1000-dimensional eigh of the Krylov solver's checks): host cores / ranks, clamped to [1, 16].
+    RVGP_HOST_THREADS overrides both."""
     import contextlib
     import os
     if _TPC[0] is None:
         try:
             from threadpoolctl import ThreadpoolController
             lw = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
-            n = int(os.environ.get("RVGP_HOST_THREADS", "0") or 0) or max(1, min(4, (os.cpu_count() or 1) // (4 * max(1, lw))))
-            _TPC[0], _TPC[1] = ThreadpoolController(), n
+            forced = int(os.environ.get("RVGP_HOST_THREADS", "0") or 0)
+            cores = os.cpu_count() or 1
+            n = forced or max(1, min(4, cores // (4 * max(1, lw))))
+            nbig = forced or max(1, min(16, cores // max(1, lw)))
+            _TPC[0], _TPC[1], _TPC[2] = ThreadpoolController(), n, nbig
         except Exception:
             _TPC[0] = False
     if not _TPC[0]:
         return contextlib.nullcontext()
-    return _TPC[0].limit(limits=_TPC[1], user_api="blas")
+    return _TPC[0].limit(limits=_TPC[2] if big else _TPC[1], user_api="blas")
 
 
 class BsrMatrix:

@@ -113,14 +113,25 @@ def one_step(X, V, train_ind, test_ind, k, device_out):
     import contextlib
     import io
     import RVGP
+    import torch
+    t0 = time.perf_counter()
     d = RVGP.create_data_object(X, vectors=V, n_eigenpairs=k, verbose=False)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
     with contextlib.redirect_stdout(io.StringIO()):
         gp = RVGP.fit(d, train_ind=train_ind, noise_variance=0.001)
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
     mean, var = gp.transform(d, test_ind, as_device=device_out)
+    torch.cuda.synchronize()
+    t3 = time.perf_counter()
     A = d._A_Lc_p
+    d.timings.update({"create_data_object_total": t1 - t0, "fit": t2 - t1, "transform": t3 - t2})
     summ = {"stats": d.stats, "timings": dict(d.timings), "sharded": bool(getattr(d, "sharded", False)),
             "d": int(A.d), "Lc_rows": int(A.nrows), "Lc_matrix_bytes": int(A.spmm_bytes(0)),
-            "gp": {"solver": getattr(gp, "solver", None), "l2_error": getattr(gp, "l2_error", None)}}
+            "gp": {"solver": getattr(gp, "solver", None), "l2_error": getattr(gp, "l2_error", None),
+                   "evaluations": getattr(getattr(gp, "_gpr", None), "n_eval", None),
+                   "row_sharded": getattr(gp, "comm", None) is not None}}
     return summ, mean, var
 
 

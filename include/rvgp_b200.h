@@ -99,6 +99,12 @@ int rvgp_bsr_mma_pack(rvgp_handle_t h, int nbrows, int d, const int32_t* indptr,
 int rvgp_bsr_spmm_mma_f64(rvgp_handle_t h, int nbrows, int d, const int32_t* kptr, const int32_t* kcols,
                           const double* afrag, const double* X, int64_t ldx, const double* W, int64_t ldw, double* Y,
                           int64_t ldy, int ncols, double alpha, double beta, double gamma);
+/* PATTERN plan (rotc == 2 below): the scalar unit-weight graph Laplacian (vals == NULL, d == 1; geometry.py:55-63) runs on the
+ * native kernel as L (x) I_2 -- a row-major (n x B) scalar panel IS a node-contiguous d = 2 panel with B/2 columns -- with no
+ * matrix values streamed at all: column words carry the 4-bit row mask of the R = 4 merge plan in bits 27..30 and the diagonal
+ * comes from deg[i] = row length - 1 (passed as `afrag`).  kptr as for d = 2 (ceil(ulen / 2) k-steps per group of 4 rows). */
+int rvgp_bsr_mma_pack_pattern(rvgp_handle_t h, int nbrows, const int32_t* indptr, const int32_t* gptr, const int32_t* uent,
+                              const int32_t* kptr, int32_t* kcols, int32_t* deg, int32_t* bad_flag);
 /* node-contiguous panels (d == 2): element (2*node+q, 2*cp+e) at Xn[node*ns + (cp*2+q)*2 + e]; beta is folded into the
  * diagonal as beta/alpha (alpha != 0).  rvgp_bsr_mma_rotc compacts the plan when every block is a scaled rotation /
  * reflection (16 doubles + sign bits per k-step; bad_flag != 0: not applicable, re-pack kcols); pass rotc = 1 then.

@@ -148,6 +148,12 @@ static int halo_step(Handle* h, const rvgp_halo_ctx* c, unsigned long long epoch
         if (rc) return rc;
     }
     const double* W = (w >= 0) ? c->E[w] : nullptr;
+    if (c->kptr != nullptr && c->rotc == 2) {
+        // scalar pattern-mode Laplacian as L (x) I_2: the row-major extended buffers ARE native panels with ncols / 2 columns
+        const int64_t ns = (int64_t)c->ncols;
+        return spmm_mma_native_dispatch(h, c->n_loc, c->kptr, c->kcols, c->afrag, 2, c->E[x], ns, W, ns, c->E[y], ns, c->ncols / 2,
+                                        alpha, beta, gamma, 0);
+    }
     if (c->kptr != nullptr) {
         const int64_t ns = 2 * (int64_t)c->ncols;
         return spmm_mma_native_dispatch(h, c->n_loc, c->kptr, c->kcols, c->afrag, c->rotc, c->E[x], ns, W, ns, c->E[y], ns, c->ncols,
@@ -159,7 +165,7 @@ static int halo_step(Handle* h, const rvgp_halo_ctx* c, unsigned long long epoch
 
 static int halo_copy_in(Handle* h, const rvgp_halo_ctx* c, const double* V, int64_t ldv, int slot) {
     if (c->n_loc == 0) return RVGP_OK;
-    if (c->kptr != nullptr) return native_convert(h, true, c->n_loc, c->ncols, const_cast<double*>(V), ldv, c->E[slot], 2 * (int64_t)c->ncols);
+    if (c->kptr != nullptr && c->rotc != 2) return native_convert(h, true, c->n_loc, c->ncols, const_cast<double*>(V), ldv, c->E[slot], 2 * (int64_t)c->ncols);
     RVGP_CUDA_OK(h, cudaMemcpy2DAsync(c->E[slot], (size_t)c->ncols * sizeof(double), V, ldv * sizeof(double),
                                       (size_t)c->ncols * sizeof(double), (size_t)c->n_loc * c->d, cudaMemcpyDeviceToDevice, h->stream));
     return RVGP_OK;
@@ -167,7 +173,7 @@ static int halo_copy_in(Handle* h, const rvgp_halo_ctx* c, const double* V, int6
 
 static int halo_copy_out(Handle* h, const rvgp_halo_ctx* c, double* V, int64_t ldv, int slot) {
     if (c->n_loc == 0) return RVGP_OK;
-    if (c->kptr != nullptr) return native_convert(h, false, c->n_loc, c->ncols, V, ldv, c->E[slot], 2 * (int64_t)c->ncols);
+    if (c->kptr != nullptr && c->rotc != 2) return native_convert(h, false, c->n_loc, c->ncols, V, ldv, c->E[slot], 2 * (int64_t)c->ncols);
     RVGP_CUDA_OK(h, cudaMemcpy2DAsync(V, ldv * sizeof(double), c->E[slot], (size_t)c->ncols * sizeof(double),
                                       (size_t)c->ncols * sizeof(double), (size_t)c->n_loc * c->d, cudaMemcpyDeviceToDevice, h->stream));
     return RVGP_OK;
@@ -177,7 +183,9 @@ static int halo_check(Handle* h, const rvgp_halo_ctx* c) {
     RVGP_REQUIRE(h, c != nullptr && c->ncols >= 2 && c->ncols % 2 == 0 && c->d >= 1, "halo: bad context (ncols must be even)");
     RVGP_REQUIRE(h, c->E[0] && c->E[1] && c->E[2], "halo: the three extended buffers are required");
     RVGP_REQUIRE(h, c->n_peers <= 32, "halo: at most 32 neighbour ranks");
-    RVGP_REQUIRE(h, c->kptr == nullptr || (c->d == 2 && c->ncols % 16 == 0), "halo: the MMA plan needs d == 2 and ncols % 16 == 0");
+    RVGP_REQUIRE(h, c->kptr == nullptr || (c->rotc != 2 && c->d == 2 && c->ncols % 16 == 0) ||
+                        (c->rotc == 2 && c->d == 1 && c->ncols % 32 == 0),
+                 "halo: the MMA plan needs d == 2 and ncols % 16 == 0, or the scalar pattern plan (rotc == 2) with ncols % 32 == 0");
     return RVGP_OK;
 }
 

@@ -524,6 +524,24 @@ extern "C" int rvgp_cheb_filter_mma_f64(rvgp_handle_t hh, int nbrows, int d, con
     RVGP_REQUIRE(h, hi > lo_cut && lo_cut > lo_spec, "cheb_filter: need lo_spec < lo_cut < hi");
     if (degree == 0 || nbrows == 0) return RVGP_OK;
     int slot = 0;
+    if (d == 1 && rotc == 2) {
+        // scalar unit-weight Laplacian as L (x) I_2 (spmm_mma.cu, AMODE 2): the ROW-MAJOR panels are already in the native
+        // layout with ncols / 2 columns, so V itself is the first buffer and nothing is converted
+        RVGP_REQUIRE(h, ncols % 32 == 0 && ldv % 2 == 0 && ldw % 2 == 0, "cheb_filter_mma (pattern): ncols % 32 == 0 and even leading dimensions");
+        double* buf[3] = {V, work0, work1};
+        int64_t ld[3] = {ldv, ldw, ldw};
+        auto apply = [&](const double* X, int64_t nsx, const double* W, int64_t nsw, double* Y, int64_t nsy, double a, double b,
+                         double g) {
+            return spmm_mma_native_dispatch(h, nbrows, kptr, kcols, afrag, 2, X, nsx, W, nsw, Y, nsy, ncols / 2, a, b, g, 0);
+        };
+        int rc = cheb_recurrence(h, apply, (int64_t)nbrows, buf, ld, ncols, degree, lo_spec, lo_cut, hi, &slot);
+        if (rc) return rc;
+        if (slot != 0) {
+            RVGP_CUDA_OK(h, cudaMemcpy2DAsync(V, ldv * sizeof(double), buf[slot], ld[slot] * sizeof(double),
+                                              (size_t)ncols * sizeof(double), (size_t)nbrows, cudaMemcpyDeviceToDevice, h->stream));
+        }
+        return RVGP_OK;
+    }
     if (d == 2 && work2 != nullptr) {
         RVGP_REQUIRE(h, ldw == ncols, "cheb_filter_mma: the native path needs contiguous work panels (ldw == ncols)");
         const int64_t ns = 2 * (int64_t)ncols;

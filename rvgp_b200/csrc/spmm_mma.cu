@@ -261,7 +261,13 @@ constexpr int ROTC_COLMASK = 0x07ffffff;     // column index bits of a ROTC colu
 // X row by a neighbouring group is an L2 hit, and the NT/32 adjacent groups of a CTA share their gathers in L1.
 // Otherwise CTA b owns the contiguous chunk of nw * groups_per_warp groups (the v2 schedule).
 // gamma * W is loaded straight into the accumulators at group start (acc = (gamma/alpha) W), so there is no load in the epilogue.
-template <int NCH, int KS, int NT, int MINB, bool ROTC>
+// AMODE selects where the A fragment comes from: 0 = full 32-double fragments, 1 = ROTC (compact rotations, above),
+// 2 = PATTERN: the unit-weight scalar graph Laplacian L (geometry.py:55-63) run as L (x) I_2 -- a ROW-MAJOR (n x B) panel of a
+// scalar block vector IS a node-contiguous panel of the d = 2 layout with B/2 columns (element (node, 4cp + 2q + e) <-> pseudo
+// component q of column 2cp + e), and every 2x2 block is a * I_2 with a in {deg_i, -1, 0}.  Nothing is streamed for the
+// matrix except the column words: bits 27..30 of word t say which of the group's 4 nodes store that neighbour (the R-bit row
+// mask of the merge plan), and the diagonal value deg_i comes from a 4-byte-per-node array (passed through `afrag`).
+template <int NCH, int KS, int NT, int MINB, int AMODE>
 __global__ void __launch_bounds__(NT, MINB)
 bsr_spmm_mma_native_kernel(int ngroups, int nbrows, const int* __restrict__ kptr, const int* __restrict__ kcols,
                            const double* __restrict__ afrag, const double* __restrict__ X, int64_t nsx,
@@ -282,17 +288,30 @@ bsr_spmm_mma_native_kernel(int ngroups, int nbrows, const int* __restrict__ kptr
     const uint64_t polX = make_policy((policy & 1) ? 1 : 0);
     const uint64_t polS = make_policy((policy & 2) ? 2 : 0);      // streams: A fragments, W
     const uint64_t polY = make_policy((policy & 4) ? 2 : ((policy & 8) ? 1 : 0));
+    constexpr bool ROTC = AMODE == 1, PATTERN = AMODE == 2;
     constexpr int AW = ROTC ? 16 : 32;              // doubles per k-step of the fragment stream
     const int aoff = ROTC ? ((r * 2 + t) * 2 + (p ^ q)) : lane;
-    const int colmask = ROTC ? ROTC_COLMASK : 0x7fffffff;
+    const int colmask = (ROTC || PATTERN) ? ROTC_COLMASK : 0x7fffffff;
+    const int* __restrict__ degs = reinterpret_cast<const int*>(afrag);     // PATTERN: diagonal values (row length - 1)
+    double degr = 0.0;
     const int64_t eoff = slab + ((2 * kq) * 2 + p) * 2;   // C fragment: (node r, component p), column pairs 8c + 2kq (+1)
 
     // Y = yscale * (W + A_eff X) with A_eff = ascale * A + afold * I:  (ascale, afold, yscale) = (alpha, beta, gamma) / gamma, or
     // (1, beta / alpha, alpha) without W.  W is loaded RAW into the accumulators and the A element is post-processed (sign,
     // scale, diagonal fold) only right before its MMA, so no arithmetic sits between a load and the next loads (in-order
     // issue: the first version stalled a full L2 latency per k-step on the sign flip placed right behind the fragment load).
-    auto load_a = [&](int s) -> double { return ldg64_stream_hint(afrag + (int64_t)s * AW + aoff, polS); };
+    auto load_a = [&](int s) -> double {
+        if (PATTERN) return 0.0;
+        return ldg64_stream_hint(afrag + (int64_t)s * AW + aoff, polS);
+    };
     auto finish_a = [&](double v, int cw, int own) -> double {
+        if (PATTERN) {
+            // a * I_2 block: only p == q lanes carry a value; -1 where node r stores this neighbour, deg_r on its own column
+            const bool is_own = (cw & (int)(0x80000000u | (unsigned)colmask)) == own;       // own == -1 when p != q
+            const bool present = (q == p) && cw >= 0 && ((cw >> (27 + r)) & 1);
+            const double a = is_own ? degr : (present ? -1.0 : 0.0);
+            return fma(ascale, a, is_own ? afold : 0.0);
+        }
         if (ROTC) {
             // [[a, -s b], [b, s a]]: (p,q) = (0,1) -> -s b ; (1,1) -> s a ; s = -1 when the flip bit is set
             const bool flip = (cw >> (27 + r)) & 1;
@@ -306,6 +325,7 @@ bsr_spmm_mma_native_kernel(int ngroups, int nbrows, const int* __restrict__ kptr
         const int s0 = __ldg(kptr + g), s1 = __ldg(kptr + g + 1);
         const int own = (q == p) ? (g * 4 + r) : -1;      // column whose A entry takes the folded beta
         const int node = g * 4 + r;
+        if (PATTERN) degr = (node < nbrows) ? (double)__ldg(degs + node) : 0.0;
         // L2 prefetch of what the warp's group `pdist` iterations ahead will stream from DRAM (its A fragments and W rows,
         // optionally its own X rows).  ncu showed the k-loop waiting a full DRAM latency per k-step (one k-step of
         // register prefetch, < 20 warps per SM); this turns those into L2 hits without holding registers.
@@ -346,7 +366,7 @@ bsr_spmm_mma_native_kernel(int ngroups, int nbrows, const int* __restrict__ kptr
             cn[j] = (s0 + KS + j < s1) ? __ldg(kcols + (int64_t)(s0 + KS + j) * 2 + t) : 0;
         }
         if (pf) {
-            if (lane == 0) prefetch_l2_bulk_hint(afrag + (int64_t)ps0 * AW, (unsigned)(ps1 - ps0) * (AW * 8u), polS);
+            if (lane == 0) { if (!PATTERN) prefetch_l2_bulk_hint(afrag + (int64_t)ps0 * AW, (unsigned)(ps1 - ps0) * (AW * 8u), polS); }
             else if (lane == 1) { prefetch_l2_line(kcols + (int64_t)ps0 * 2); prefetch_l2_line(kcols + (int64_t)ps1 * 2 - 1); }
             else if (lane >= 4 && lane < 12) {
                 const int pn = gp * 4 + (lane & 3);
@@ -390,6 +410,29 @@ bsr_spmm_mma_native_kernel(int ngroups, int nbrows, const int* __restrict__ kptr
             }
         }
     }
+}
+
+// PATTERN packing (AMODE 2): k-steps of 2 union neighbours straight from the R = 4 merge plan; column word = column |
+// row mask << 27 (which of the group's 4 nodes store it) | bit 31 on padding; deg[i] = row length - 1 (the self loop).
+__global__ void mma_pack_pattern_kernel(int ngroups, const int* __restrict__ gptr, const int2* __restrict__ uent,
+                                        const int* __restrict__ kptr, int* __restrict__ kcols, int* __restrict__ bad) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ngroups) return;
+    const int u0 = gptr[g], ulen = gptr[g + 1] - u0;
+    const int s0 = kptr[g], ns = kptr[g + 1] - s0;
+    for (int s = 0; s < ns; ++s) {
+        for (int t = 0; t < 2; ++t) {
+            const int u = s * 2 + t;
+            const int2 ent = uent[u0 + (u < ulen ? u : ulen - 1)];
+            if ((ent.x & ROTC_COLMASK) != ent.x) atomicOr(bad, 2);          // column index does not fit in 27 bits
+            kcols[(int64_t)(s0 + s) * 2 + t] = (u < ulen) ? (ent.x | ((ent.y & 15) << 27)) : (ent.x | (int)0x80000000);
+        }
+    }
+}
+
+__global__ void row_degree_kernel(int n, const int* __restrict__ indptr, int* __restrict__ deg) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) deg[i] = indptr[i + 1] - indptr[i] - 1;
 }
 
 // ROTC packing: afrag (32 doubles per k-step, fragment order) -> 16 doubles (a, b per (node r, neighbour t)) + flip bits
@@ -473,10 +516,13 @@ int spmm_mma_native_dispatch(Handle* h, int nbrows, const int* kptr, const int* 
         const int nw_ = NT / 32;                                                                                       \
         const int gx = gpw > 0 ? cdiv(ngroups, nw_ * gpw) : (int)std::min<long long>(cdiv(ngroups, nw_), std::max(1, h->sm_count * MINB / nslab)); \
         dim3 grid(gx, nslab);                                                                                          \
-        if (rotc) bsr_spmm_mma_native_kernel<NCH, KS, NT, MINB, true><<<grid, NT, 0, h->stream>>>(                     \
+        if (rotc == 2) bsr_spmm_mma_native_kernel<NCH, KS, NT, MINB, 2><<<grid, NT, 0, h->stream>>>(                   \
             ngroups, nbrows, kptr, kcols, afrag, X, nsx, W, nsw, Y, nsy, ascale, afold, yscale, has_w, gpw, gpw <= 0,           \
             h->mma_prefetch, h->mma_stream_policy, reverse);                                                           \
-        else bsr_spmm_mma_native_kernel<NCH, KS, NT, MINB, false><<<grid, NT, 0, h->stream>>>(                         \
+        else if (rotc) bsr_spmm_mma_native_kernel<NCH, KS, NT, MINB, 1><<<grid, NT, 0, h->stream>>>(                   \
+            ngroups, nbrows, kptr, kcols, afrag, X, nsx, W, nsw, Y, nsy, ascale, afold, yscale, has_w, gpw, gpw <= 0,           \
+            h->mma_prefetch, h->mma_stream_policy, reverse);                                                           \
+        else bsr_spmm_mma_native_kernel<NCH, KS, NT, MINB, 0><<<grid, NT, 0, h->stream>>>(                             \
             ngroups, nbrows, kptr, kcols, afrag, X, nsx, W, nsw, Y, nsy, ascale, afold, yscale, has_w, gpw, gpw <= 0,           \
             h->mma_prefetch, h->mma_stream_policy, reverse);                                                           \
     } while (0)
@@ -555,4 +601,23 @@ extern "C" int rvgp_bsr_mma_rotc(rvgp_handle_t hh, int64_t nk, const double* afr
 extern "C" int rvgp_panel_native_f64(rvgp_handle_t hh, int to_native, int nbrows, int ncols, double* V, int64_t ldv,
                                      double* Xn, int64_t ns) {
     return native_convert(H(hh), to_native != 0, nbrows, ncols, V, ldv, Xn, ns);
+}
+
+// PATTERN plan of the scalar unit-weight Laplacian for the native kernel (rotc == 2 in rvgp_bsr_spmm_mma_native_f64 /
+// rvgp_cheb_filter_mma_f64): gptr / uent from rvgp_bsr_merge_plan with R = 4; kptr (ngroups + 1) = exclusive prefix of
+// ceil(ulen_g / 2); kcols: 2 * kptr[ngroups] int32; deg: nbrows int32 (pass it as `afrag`).  bad_flag (device int32, zeroed
+// here): bit1 = a column index needs more than 27 bits.
+extern "C" int rvgp_bsr_mma_pack_pattern(rvgp_handle_t hh, int nbrows, const int32_t* indptr, const int32_t* gptr,
+                                         const int32_t* uent, const int32_t* kptr, int32_t* kcols, int32_t* deg,
+                                         int32_t* bad_flag) {
+    Handle* h = H(hh);
+    RVGP_CUDA_OK(h, cudaMemsetAsync(bad_flag, 0, sizeof(int), h->stream));
+    const int ngroups = cdiv(nbrows, 4);
+    if (ngroups == 0) return RVGP_OK;
+    mma_pack_pattern_kernel<<<cdiv(ngroups, 128), 128, 0, h->stream>>>(ngroups, gptr, reinterpret_cast<const int2*>(uent), kptr,
+                                                                        kcols, bad_flag);
+    RVGP_LAUNCH_OK(h, "mma_pack_pattern_kernel");
+    row_degree_kernel<<<cdiv(nbrows, 256), 256, 0, h->stream>>>(nbrows, indptr, deg);
+    RVGP_LAUNCH_OK(h, "row_degree_kernel");
+    return RVGP_OK;
 }

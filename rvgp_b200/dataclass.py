@@ -237,6 +237,9 @@ class data:
         eig_Lc = smallest_eigenpairs_paired if self.stats["paired"] else smallest_eigenpairs
         if dim_man == 2 and not shard and n >= 64 and os.environ.get("RVGP_SPMM_MMA", "1") != "0":
             self.stats["spmm_mma"] = A_eig.enable_mma() is not None
+        if not shard and os.environ.get("RVGP_SPMM_MMA_L", "1") != "0":
+            # K9 for the scalar Laplacian: the same FP64-MMA kernel as L (x) I_2, no matrix values streamed (spmm_mma.cu AMODE 2)
+            self.stats["spmm_mma_L"] = A_L.enable_mma_pattern() is not None
         self.timings["connections"] = tick() - t0
 
         say('Compute eigendecompositions')
@@ -273,6 +276,8 @@ class data:
             S_Lc = ShardedBsr(plan, dim_man, plan.local_values(A_eig.vals), comm)
             if dim_man == 2 and os.environ.get("RVGP_SPMM_MMA", "1") != "0" and os.environ.get("RVGP_PEER_HALO", "1") != "0":
                 self.stats["spmm_mma"] = S_Lc.enable_mma() is not None
+            if os.environ.get("RVGP_SPMM_MMA_L", "1") != "0" and os.environ.get("RVGP_PEER_HALO", "1") != "0":
+                self.stats["spmm_mma_L"] = S_L.enable_mma() is not None
             counts = [int(bounds[r + 1] - bounds[r]) for r in range(world)]
             self.stats["halo"] = dict(n_loc=plan.n_loc, n_halo=plan.n_halo, send=sum(plan.send_counts))
             try:

@@ -252,7 +252,8 @@ class PeerHalo:
         self.epoch = 1
         L = op.local
         mp = L.mma if (d == 2 and getattr(L, "mma", None) is not None and self.ncols % 16 == 0) else None
-        self.kernel = "mma_native" if mp is not None else "gather"
+        pat = L.mma_pattern if (d == 1 and getattr(L, "mma_pattern", None) is not None and self.ncols % 32 == 0) else None
+        self.kernel = "mma_native" if mp is not None else ("mma_native_pattern" if pat is not None else "gather")
 
         class Ctx(ctypes.Structure):
             _fields_ = [("n_loc", ctypes.c_int32), ("n_halo", ctypes.c_int32), ("d", ctypes.c_int32), ("ncols", ctypes.c_int32),
@@ -273,6 +274,8 @@ class PeerHalo:
             c.kcols = (mp["kcols_c"] if rotc else mp["kcols"]).data_ptr()
             c.afrag = (mp["afrag_c"] if rotc else mp["afrag"]).data_ptr()
             c.rotc = int(rotc)
+        elif pat is not None:            # scalar unit-weight Laplacian on the MMA kernel (spmm_mma.cu AMODE 2): no values streamed
+            c.kptr, c.kcols, c.afrag, c.rotc = pat["kptr"].data_ptr(), pat["kcols"].data_ptr(), pat["deg"].data_ptr(), 2
         c.n_peers = len(peers)
         for s in range(3):
             c.E[s] = self.E_ptrs[s][rank]
@@ -367,9 +370,19 @@ class ShardedBsr:
         return "gather + nccl halo"
 
     def enable_mma(self, on=True, h=None):
-        """FP64-MMA SpMM for the local rows (d == 2); only used by the peer-memory path."""
-        self.mma = self.local.enable_mma(on, h=h) if self.d == 2 else None
+        """FP64-MMA SpMM for the local rows (d == 2: compact-rotation plan; d == 1 pattern mode: L (x) I_2 plan); only used by
+        the peer-memory path."""
+        if self.d == 2:
+            self.mma = self.local.enable_mma(on, h=h)
+        elif self.d == 1 and self.vals is None:
+            self.mma = self.local.enable_mma_pattern(on, h=h)
+        else:
+            self.mma = None
         return self.mma
+
+    @property
+    def mma_pattern(self):
+        return self.local.mma_pattern
 
     def _peer_for(self, ncols):
         """PeerHalo for this panel width, built collectively on first use (all ranks take the same path)."""

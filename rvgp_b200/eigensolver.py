@@ -140,6 +140,39 @@ class BsrMatrix:
         self._mma_plan = plan
         return plan
 
+    mma_pattern = None        # PATTERN plan of the scalar unit-weight Laplacian on the native MMA kernel (spmm_mma.cu, AMODE 2)
+
+    def enable_mma_pattern(self, on=True, h=None):
+        """Scalar unit-weight Laplacian (d == 1, vals None): run the Chebyshev filter on the FP64-MMA native kernel as L (x) I_2.
+        A row-major (n x B) panel is already in that kernel's layout, and no matrix values are streamed (k-step column words carry
+        the row masks; the diagonal is row length - 1)."""
+        if not on or self.d != 1 or self.vals is not None or self.nbrows < 64:
+            self.mma_pattern = None
+            return None
+        if self.mma_pattern is None:
+            h = h or get_handle(self.indptr.device.index)
+            dev = self.indptr.device
+            mp = self.build_merge_plan(4, h=h)
+            gptr = mp["gptr"]
+            ns = (gptr[1:] - gptr[:-1] + 1) // 2
+            kptr = torch.zeros(gptr.numel(), dtype=torch.int32, device=dev)
+            kptr[1:] = torch.cumsum(ns, 0).to(torch.int32)
+            nk = int(kptr[-1].item())
+            kcols = torch.empty(max(1, nk * 2), dtype=torch.int32, device=dev)
+            deg = torch.empty(self.nbrows, dtype=torch.int32, device=dev)
+            bad = torch.zeros(1, dtype=torch.int32, device=dev)
+            h.call("rvgp_bsr_mma_pack_pattern", self.nbrows, self.indptr, gptr, mp["uent"], kptr, kcols, deg, bad)
+            self.__dict__.get("_mplans", {}).pop(4, None)
+            if int(bad.item()) != 0:
+                return None
+            self.mma_pattern = dict(kptr=kptr, kcols=kcols, deg=deg, ksteps=nk, reuse=mp["reuse"])
+        return self.mma_pattern
+
+    def _mma_pattern_ok(self, ncols, Vp, w0, w1):
+        if self.mma_pattern is None or ncols % 32:
+            return False
+        return all(t.stride(0) % 2 == 0 and t.data_ptr() % 16 == 0 for t in (Vp, w0, w1))
+
     def enable_mma(self, on=True, h=None, rowmajor=False):
         """Route cheb_filter (d == 2: node-contiguous panels) through the FP64-MMA kernel whenever shapes / alignment
         allow it; ``rowmajor`` additionally routes single products through the row-major MMA kernel (experiment)."""
@@ -189,6 +222,15 @@ class BsrMatrix:
                float(beta), float(gamma), int(bool(reverse)))
         return Yn
 
+    def spmm_pattern(self, X, Y, alpha=1.0, beta=0.0, gamma=0.0, W=None, h=None):
+        """Y = alpha L X + beta X + gamma W for ROW-MAJOR scalar panels through the PATTERN plan (ncols % 32 == 0)."""
+        h = h or get_handle(X.device.index)
+        mp = self.mma_pattern
+        h.call("rvgp_bsr_spmm_mma_native_f64", self.nbrows, mp["kptr"], mp["kcols"], mp["deg"], 2, X, I64(X.stride(0)), W,
+               I64(W.stride(0) if W is not None else 0), Y, I64(Y.stride(0)), int(X.shape[1] // 2), float(alpha), float(beta),
+               float(gamma), 0)
+        return Y
+
     # ---- row-group merge plan (union column lists; input of the MMA k-step plan) --------------------------------
     def build_merge_plan(self, R=4, h=None):
         """Union column lists of groups of R consecutive block rows (rvgp_bsr_merge_plan)."""
@@ -222,6 +264,11 @@ class BsrMatrix:
             h.call("rvgp_cheb_filter_mma_f64", self.nbrows, self.d, mp["kptr"], mp["kcols_c"] if rotc else mp["kcols"],
                    mp["afrag_c"] if rotc else mp["afrag"], int(rotc), Vp, I64(Vp.stride(0)), w0, w1, w2, I64(ncols),
                    int(ncols), int(degree), float(lo_spec), float(lo_cut), float(hi))
+            return
+        if self._mma_pattern_ok(ncols, Vp, w0, w1):
+            mp = self.mma_pattern
+            h.call("rvgp_cheb_filter_mma_f64", self.nbrows, 1, mp["kptr"], mp["kcols"], mp["deg"], 2, Vp, I64(Vp.stride(0)), w0, w1,
+                   None, I64(w0.stride(0)), int(ncols), int(degree), float(lo_spec), float(lo_cut), float(hi))
             return
         if self.d_code == -2 and aligned:
             dc, ix, vl = self.d_code, self.indices_k, self.vals_k
@@ -369,7 +416,7 @@ def smallest_eigenpairs(A, k, upper_bound, lower_bound=0.0, tol=1e-12, nex=None,
     w2 = None
     if isinstance(A, BsrMatrix) and A.mma is not None and A.d == 2:
         w2 = torch.empty((N, panel), dtype=torch.float64, device=dev)
-    st["spmm_kernel"] = "mma_native" if w2 is not None else "gather"
+    st["spmm_kernel"] = "mma_native" if w2 is not None else ("mma_native_pattern" if getattr(A, "mma_pattern", None) is not None else "gather")
     Gd = torch.empty((m, m), dtype=torch.float64, device=dev)
     Hd = torch.empty((m, m), dtype=torch.float64, device=dev)
     Cd = torch.empty((m, m), dtype=torch.float64, device=dev)

@@ -61,13 +61,24 @@ class _Chol:
 class DeviceGPR:
     """GP regression with kernel K = Phi diag(S) Phi^T + noise I on rows X (M, k), single output column Y (M, 1)."""
 
-    def __init__(self, X, Y, solver="auto"):
+    def __init__(self, X, Y, solver="auto", comm=None):
+        """comm (distributed.Comm, world > 1): X / Y are THIS RANK's training rows; the rank-k path needs exactly one
+        all-reduce of [Phi y]^T [Phi y] ((k+1)^2 doubles), after which every rank holds the same G, b, y^T y and runs the same
+        host optimisation.  The dense M x M path cannot be row-sharded: callers pass comm only with lowrank."""
         self.X, self.Y = X.contiguous(), Y.contiguous().reshape(-1, 1)
-        self.M, self.k = self.X.shape
+        self.M_local, self.k = self.X.shape
+        self.M = self.M_local
         self.dev = X.device
         self.h = get_handle(self.dev.index)
+        self.comm = comm if (comm is not None and comm.world > 1) else None
+        if self.comm is not None:
+            t = torch.tensor([self.M_local], dtype=torch.int64, device=self.dev)
+            self.comm.allreduce_(t)
+            self.M = int(t.item())
         if solver == "auto":
             solver = "lowrank" if self.M >= 2 * self.k else "dense"
+        if self.comm is not None and solver != "lowrank":
+            raise ValueError("row-sharded GP needs the rank-k solver (global M >= 2 k)")
         self.solver = solver
         self.n_eval = 0
         if solver == "lowrank":
@@ -76,12 +87,16 @@ class DeviceGPR:
     # ---- K15: tall-skinny Gram pass --------------------------------------------------------------------
     def _init_lowrank(self):
         h, M, k = self.h, self.M, self.k
-        XY = torch.cat([self.X, self.Y], dim=1).contiguous()          # (M, k+1): one pass gives G, b and y^T y
+        Ml = self.M_local
+        XY = torch.cat([self.X, self.Y], dim=1).contiguous()          # (M_local, k+1): one pass gives G, b and y^T y
         kk = k + 1
-        split = max(1, min(64, M // 2048))
+        split = max(1, min(64, Ml // 2048))
         ws = torch.empty(split * kk * kk, dtype=torch.float64, device=self.dev)
-        Gd = torch.empty((kk, kk), dtype=torch.float64, device=self.dev)
-        _dgemm(h, kk, kk, M, XY, XY.stride(0), 0, XY, XY.stride(0), 0, Gd, Gd.stride(0), split_k=split, ws=ws)
+        Gd = torch.zeros((kk, kk), dtype=torch.float64, device=self.dev)
+        if Ml > 0:
+            _dgemm(h, kk, kk, Ml, XY, XY.stride(0), 0, XY, XY.stride(0), 0, Gd, Gd.stride(0), split_k=split, ws=ws)
+        if self.comm is not None:
+            self.comm.allreduce_(Gd)                                  # the ONE collective of the row-sharded fit
         Gh = Gd.cpu().numpy()
         Gh = 0.5 * (Gh + Gh.T)
         self.G, self.b, self.yy = Gh[:k, :k].copy(), Gh[:k, k].copy(), float(Gh[k, k])

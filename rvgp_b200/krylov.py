@@ -245,7 +245,7 @@ def krylov_eigenpairs(A, k, upper_bound, cut, lam_k, paired=False, tol=1e-12, bl
     w1 = torch.empty((N, b), dtype=torch.float64, device=dev)
     w2 = torch.empty((N, b), dtype=torch.float64, device=dev) if (isinstance(A, BsrMatrix) and A.mma is not None and A.d == 2) else None
     Wb = torch.empty((N, b), dtype=torch.float64, device=dev)             # the block being filtered (contiguous panel)
-    st["spmm_kernel"] = "mma_native" if w2 is not None else "gather"
+    st["spmm_kernel"] = "mma_native" if w2 is not None else ("mma_native_pattern" if getattr(A, "mma_pattern", None) is not None else "gather")
     ops = FieldOps(h, N, cap, b, dev, comm, paired)
     cdt = np.complex128 if paired else np.float64
     T = np.zeros((cap, cap), dtype=cdt)

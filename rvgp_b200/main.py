@@ -134,6 +134,9 @@ class _Model:
         else:
             # like the reference, ALWAYS rows of evecs_Lc (main.py:104-106), whatever the kernel was trained on
             nodes = _as_node_indices(test_ind, data.n)
+            comm = getattr(self, "comm", None)
+            if comm is not None and comm.world > 1:
+                return self._transform_sharded(data, nodes, comm, as_device)
             test_x = _node_rows_device(data, nodes)
             n_out = len(nodes)
         with _nvtx.stage('transform:predict_f'):
@@ -145,18 +148,44 @@ class _Model:
         return f_pred_mean, f_pred_std
 
 
+def _rank_chunk(n_items, comm):
+    """Contiguous share of range(n_items) for this rank and the share sizes of all ranks."""
+    bounds = [(n_items * r) // comm.world for r in range(comm.world + 1)]
+    return bounds[comm.rank], bounds[comm.rank + 1], [bounds[r + 1] - bounds[r] for r in range(comm.world)]
+
+
+def _transform_sharded(self, data, nodes, comm, as_device):
+    """Row-sharded ``transform`` (SPMD: every rank calls it with the same arguments): each rank predicts its contiguous share
+    of the test nodes, one all-gather returns the complete (n_test, D) mean / variance on every rank."""
+    a, b, counts = _rank_chunk(len(nodes), comm)
+    test_x = _node_rows_device(data, nodes[a:b])
+    with _nvtx.stage('transform:predict_f'):
+        m, v = self.predict_f(test_x)
+    D = data.device_array("evecs_Lc").shape[0] // data.n
+    both = torch.cat([m.tensor.reshape(b - a, D), v.tensor.reshape(b - a, D)], dim=1).contiguous()
+    full = comm.allgather_rows(both, counts)
+    mean, var = full[:, :D].contiguous(), full[:, D:].contiguous()
+    if as_device:
+        return mean, var
+    return mean.cpu().numpy(), var.cpu().numpy()
+
+
+_Model._transform_sharded = _transform_sharded
+
+
 class manifold_GPR(_Model):
     """GP regression model (replaces the gpflow.models.GPR subclass, main.py:98-116)."""
 
-    def __init__(self, data, kernel, mean_function=None, noise_variance=None, likelihood=None, solver="auto"):
+    def __init__(self, data, kernel, mean_function=None, noise_variance=None, likelihood=None, solver="auto", comm=None):
         # like the reference, mean_function / noise_variance / likelihood are ignored (main.py:100)
         X, Y = data
         self.data = (to_device_f64(X), to_device_f64(Y))
         self.kernel = kernel
         self.likelihood = _Gaussian()
+        self.comm = comm
         self._spectral = isinstance(kernel, ManifoldKernel) and self.data[1].shape[1] == 1 and solver != "general"
         if self._spectral:
-            self._gpr = DeviceGPR(self.data[0], self.data[1], solver=solver)
+            self._gpr = DeviceGPR(self.data[0], self.data[1], solver=solver, comm=comm)
             self.solver = self._gpr.solver
         else:
             self._gpr = DenseGPR(self.data[0], self.data[1], kernel)
@@ -284,6 +313,23 @@ def train_gp(data,
     # split training and test set: sklearn on an index array gives the same rows as splitting the arrays
     # (main.py:40-45); bit-exact host RNG, only indices go to the GPU
     tr, te = train_test_split(np.arange(len(train_nodes)), test_size=test_size, random_state=seed)
+    # multi-GPU (data.sharded: SPMD, every rank makes the same calls): the rank-k spectral GP is sharded over TRAINING NODES --
+    # each rank gathers / multiplies only its contiguous share of the rows, one all-reduce of Phi^T [Phi y] joins them, and every
+    # rank then runs the identical 4-scalar host optimisation.  Other model kinds stay replicated.
+    comm = None
+    if (getattr(data, "sharded", False) and feature == "evecs_Lc" and n_inducing_points is None
+            and isinstance(kernel, ManifoldKernel) and dim * len(tr) >= 2 * data.device_array("evecs_Lc").shape[1]
+            and solver in ("auto", "lowrank")):
+        from .distributed import Comm
+        comm = Comm()
+        if comm.world > 1:
+            a, b, _ = _rank_chunk(len(tr), comm)
+            tr_all, te_all = tr, te
+            tr = tr[a:b]
+            a2, b2, _ = _rank_chunk(len(te), comm)
+            te = te[a2:b2]
+        else:
+            comm = None
     if feature == "evecs_Lc":
         in_train = _node_rows_device(data, train_nodes[tr])             # (n_tr * D, k)
         in_test = _node_rows_device(data, train_nodes[te])
@@ -298,7 +344,7 @@ def train_gp(data,
     P.set_default_positive_minimum(positivity_constraint)
 
     if n_inducing_points is None:
-        GP = manifold_GPR((in_train, out_train), kernel, noise_variance=noise_variance, solver=solver)
+        GP = manifold_GPR((in_train, out_train), kernel, noise_variance=noise_variance, solver=solver, comm=comm)
     else:
         # inducing points: furthest-point sampling in FEATURE space (main.py:60-61), on the device (K1, D = k)
         from .fps import furthest_point_sampling_device
@@ -318,7 +364,15 @@ def train_gp(data,
 
     # test
     out_pred, _ = GP.predict_f(in_test)
-    l2_error = np.linalg.norm(out_test.cpu().numpy() - out_pred.numpy(), axis=1).mean()
+    if comm is not None:
+        # mean over ALL held-out rows: sum of this rank's row norms, one small all-reduce
+        part = torch.linalg.vector_norm(out_test - out_pred.tensor, dim=1).sum().reshape(1)
+        cnt = torch.tensor([float(out_test.shape[0])], dtype=torch.float64, device=part.device)
+        both = torch.cat([part, cnt])
+        comm.allreduce_(both)
+        l2_error = float(both[0].item() / max(both[1].item(), 1.0))
+    else:
+        l2_error = np.linalg.norm(out_test.cpu().numpy() - out_pred.numpy(), axis=1).mean()
     print("Relative l2 error is {}".format(l2_error))
     GP.l2_error = float(l2_error)
     return GP

@@ -50,8 +50,10 @@ def test_hot_mma_spmm_kernel_does_not_spill():
     g.build()
     log = os.path.join(os.path.dirname(_cabi.LIB_PATH), "..", "build", "spmm_mma.o.log")
     txt = open(log).read()
-    i = txt.find("Function properties for _ZN4rvgp26bsr_spmm_mma_native_kernelILi4ELi2ELi256ELi2ELb1E")
-    assert i >= 0, "hot instantiation not found in the ptxas log"
-    chunk = txt[i:i + 600]
-    assert "0 bytes spill stores, 0 bytes spill loads" in chunk, chunk
-    assert int(re.search(r"Used (\d+) registers", chunk).group(1)) <= 128
+    # AMODE 1 = compact rotations (connection Laplacian), AMODE 2 = pattern mode (scalar Laplacian as L (x) I_2)
+    for amode in (1, 2):
+        i = txt.find("Function properties for _ZN4rvgp26bsr_spmm_mma_native_kernelILi4ELi2ELi256ELi2ELi%dE" % amode)
+        assert i >= 0, "hot instantiation (AMODE %d) not found in the ptxas log" % amode
+        chunk = txt[i:i + 600]
+        assert "0 bytes spill stores, 0 bytes spill loads" in chunk, chunk
+        assert int(re.search(r"Used (\d+) registers", chunk).group(1)) <= 128

@@ -298,3 +298,51 @@ def test_cheb_filter_mma_matches_gather(degree):
         assert np.abs(outs[0][:, :32] - V0[:, :32].cpu().numpy()).max() == 0.0
         assert np.abs(outs[0][:, 64:] - V0[:, 64:].cpu().numpy()).max() == 0.0
         assert np.abs(outs[0] - outs[1]).max() <= 1e-11 * np.abs(outs[0]).max()
+
+
+@pytest.mark.parametrize("case", ["sphere_n2000_k50", "flat3torus_R6_n900_k24", "torus_n600_k20", "sheet_R20_n500_k16"])
+@pytest.mark.parametrize("ncols", [32, 64, 96, 128])
+def test_spmm_mma_pattern_matches_scipy(case, ncols):
+    """K9 for the scalar Laplacian on the FP64-MMA native kernel (L (x) I_2, no matrix values streamed; spmm_mma.cu AMODE 2):
+    equals SciPy's L @ X on ROW-MAJOR panels, plain and fused (alpha, beta, gamma), contiguous and strided."""
+    g = load_golden(case)
+    A, S = _bsr_from_golden(g, "L")
+    assert A.enable_mma_pattern() is not None
+    rng = np.random.default_rng(3)
+    X = rng.normal(size=(A.nrows, ncols))
+    W = rng.normal(size=(A.nrows, ncols))
+    Xd, Wd = torch.from_numpy(X).to(_dev()), torch.from_numpy(W).to(_dev())
+    Yd = torch.full_like(Xd, float("nan"))
+    A.spmm_pattern(Xd, Yd)
+    ref = S @ X
+    assert np.abs(Yd.cpu().numpy() - ref).max() <= 1e-13 * np.abs(ref).max()
+    A.spmm_pattern(Xd, Yd, alpha=0.7, beta=-1.3, gamma=0.25, W=Wd)
+    ref2 = 0.7 * ref - 1.3 * X + 0.25 * W
+    assert np.abs(Yd.cpu().numpy() - ref2).max() <= 1e-13 * np.abs(ref2).max()
+    A.spmm_pattern(Xd, Yd, alpha=2.0, beta=0.5)                          # beta folded into the diagonal, no W
+    assert np.abs(Yd.cpu().numpy() - (2.0 * ref + 0.5 * X)).max() <= 1e-13 * np.abs(ref).max()
+    big = torch.from_numpy(rng.normal(size=(A.nrows, ncols + 40))).to(_dev())      # a panel inside a wider block vector
+    out = torch.full_like(big, float("nan"))
+    A.spmm_pattern(big[:, 8:8 + ncols], out[:, 16:16 + ncols])
+    refb = S @ big[:, 8:8 + ncols].cpu().numpy()
+    assert np.abs(out[:, 16:16 + ncols].cpu().numpy() - refb).max() <= 1e-13 * np.abs(refb).max()
+    assert bool(torch.isnan(out[:, :16]).all()) and bool(torch.isnan(out[:, 16 + ncols:]).all())
+
+
+@pytest.mark.parametrize("degree", [1, 2, 9, 40])
+def test_cheb_filter_mma_pattern_matches_gather(degree):
+    g = load_golden("sphere_n2000_k50")
+    A, _ = _bsr_from_golden(g, "L")
+    V0 = torch.from_numpy(np.random.default_rng(2).normal(size=(A.nrows, 192))).to(_dev())
+    outs = []
+    for on in (False, True):
+        A.enable_mma_pattern(on)
+        V = V0.clone()
+        w0 = torch.empty((A.nrows, 64), dtype=torch.float64, device=_dev()); w1 = torch.empty_like(w0)
+        if on:
+            assert A._mma_pattern_ok(64, V[:, 64:128], w0, w1)
+        A.cheb_filter(V[:, 64:128], w0, w1, 64, degree, 0.0, 3.0, 40.0)
+        outs.append(V.cpu().numpy())
+    assert np.abs(outs[1][:, :64] - V0[:, :64].cpu().numpy()).max() == 0.0
+    assert np.abs(outs[1][:, 128:] - V0[:, 128:].cpu().numpy()).max() == 0.0
+    assert np.abs(outs[0] - outs[1]).max() <= 1e-11 * np.abs(outs[0]).max()

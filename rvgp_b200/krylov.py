@@ -46,8 +46,9 @@ class FieldOps:
         self.h, self.N, self.cap, self.b, self.dev, self.comm, self.cplx = h, N, cap, b, dev, comm, cplx
         self.Cd = torch.empty((cap, b), dtype=torch.float64, device=dev)          # Gram output / coefficient upload (real part)
         self.Ci = torch.empty((cap, b), dtype=torch.float64, device=dev) if cplx else None
-        self.split = max(1, min(64, (4 * h.sm_count) // max(1, math.ceil(cap / 128)), N // 2048 if N >= 4096 else 1))
-        self.ws = torch.empty(self.split * cap * b, dtype=torch.float64, device=dev)
+        # split-K workspace of the Gram products: the (cur x b) outputs have few 128 x 64 tiles, so the reduction dimension
+        # (the N rows) is split until ~3 CTAs per SM are in flight: split * tiles <= 3 * SMs
+        self.ws = torch.empty(3 * h.sm_count * 128 * 64 + cap * b, dtype=torch.float64, device=dev)
         self.tmp = torch.empty((N, b), dtype=torch.float64, device=dev)           # J W / V Im(C) scratch
         self.flops = 0.0
 
@@ -55,8 +56,10 @@ class FieldOps:
     def _gram_real(self, Vc, W, out):
         cur, nb = Vc.shape[1], W.shape[1]
         o = out[:cur, :nb]
+        tiles = math.ceil(cur / 128) * math.ceil(nb / 64)
+        split = max(1, min(256, (3 * self.h.sm_count) // tiles, self.N // 4096 if self.N >= 8192 else 1))
         self.h.call("rvgp_dgemm_f64", int(cur), int(nb), I64(self.N), 1.0, Vc, I64(Vc.stride(0)), 0, W, I64(W.stride(0)), 0, None,
-                    o, I64(out.stride(0)), int(self.split), self.ws)
+                    o, I64(out.stride(0)), int(split), self.ws)
         self.flops += 2.0 * self.N * cur * nb
         return o
 
@@ -119,14 +122,18 @@ class FieldOps:
         return 0.5 * (G + G.T)
 
     def right_multiply(self, Vc, M, out):
-        """out (N x p) = Vc @ M for a host matrix M (cur x p), real or complex."""
+        """out (N x p) = Vc @ M for an (cur x p) matrix M, real or complex, on the host (NumPy) or on the device (torch)."""
         cur, p = M.shape
-        Md = torch.from_numpy(np.ascontiguousarray(M.real if self.cplx else M, dtype=np.float64)).to(self.dev)
+        if isinstance(M, torch.Tensor):
+            Md = (M.real if M.is_complex() else M).to(torch.float64).contiguous()
+            Mi = M.imag.to(torch.float64).contiguous() if (self.cplx and M.is_complex()) else None
+        else:
+            Md = torch.from_numpy(np.ascontiguousarray(M.real if self.cplx else M, dtype=np.float64)).to(self.dev)
+            Mi = torch.from_numpy(np.ascontiguousarray(M.imag, dtype=np.float64)).to(self.dev) if self.cplx else None
         self.h.call("rvgp_dgemm_f64", int(self.N), int(p), I64(cur), 1.0, Vc, I64(Vc.stride(0)), 1, Md, I64(Md.stride(0)), 0, None,
                     out, I64(out.stride(0)), 1, None)
         self.flops += 2.0 * self.N * cur * p
-        if self.cplx:
-            Mi = torch.from_numpy(np.ascontiguousarray(M.imag, dtype=np.float64)).to(self.dev)
+        if Mi is not None:
             for c0 in range(0, p, self.b):                   # out += J (Vc Im M), one scratch panel at a time
                 c1 = min(p, c0 + self.b)
                 t = self.tmp[:, :c1 - c0]
@@ -174,6 +181,10 @@ class FieldOps:
         if not hasattr(self, "_sw"):
             self._sw = torch.empty((self.N, self.b), dtype=torch.float64, device=self.dev)
         return self._sw[:, :like.shape[1]]
+
+
+import os as _os
+_HOST_EIGH = _os.environ.get("RVGP_HOST_EIGH", "0") == "1"
 
 
 def _filter_degree(cut, lam_k, hi, lo, nats):
@@ -264,21 +275,32 @@ def krylov_eigenpairs(A, k, upper_bound, cut, lam_k, paired=False, tol=1e-12, bl
     retry_cut = None
     fresh_restart = False
     rho_cut = 1.0 / math.cosh(d * g0)                    # level of the damped part of the spectrum under B
-    # measured (C2 / C4, real and paired): convergence ~ 46 / f blocks after the start-up phase (basis dimension < kw).  Each
-    # check costs a host eigh of the projected matrix (~ 3-4 blocks' worth of GPU time at C4), so the first one is placed where
+    # measured (C2 / C4, real and paired): convergence ~ 46-52 / f blocks after the start-up phase (basis dimension < kw).  A
+    # check costs one m x m eigh on the GPU (~20 ms at C4, a fifth of a block), so the first one is placed a little before
     # convergence is expected and the following ones where the Lanczos estimate says the tolerance will be reached
-    next_check = math.ceil(kw / b) + max(2, math.ceil(46.0 / f))
+    next_check = math.ceil(kw / b) + max(2, math.ceil(40.0 / f))
 
     def ritz(m):
-        """Ritz pairs of T[:m, :m], largest first (largest of B = smallest of A), and Lanczos residual estimates."""
+        """Ritz pairs of T[:m, :m], largest first (largest of B = smallest of A), and the Lanczos residual estimates
+        ||R Y_last[:, i]||.  The m x m Hermitian eigenproblem runs on the GPU (torch.linalg.eigh = cuSOLVER; measured on the
+        B200 box, tools/eigh_probe.py: 20 ms for real m = 1280 and 14 ms for complex m = 960, against 86 / 102 ms for LAPACK on
+        16 host cores and 266 / 685 ms on one -- and under torchrun every rank only has a few cores).  Y stays on the device
+        for the basis rotation; the host gets the m eigenvalues and m residual estimates.  RVGP_HOST_EIGH=1: host LAPACK."""
         t0 = time.perf_counter()
-        with _lapack_ctx(big=True):
-            th, Y = scipy.linalg.eigh(T[:m, :m], driver="evd", check_finite=False)
-        st["t_host"] += time.perf_counter() - t0
-        th, Y = th[::-1], Y[:, ::-1]
-        Rc = T[m:m + b, m - b:m]
-        resB = np.linalg.norm(Rc @ Y[m - b:m, :], axis=0)
-        return th, Y, resB
+        if _HOST_EIGH:
+            with _lapack_ctx(big=True):
+                th, Y = scipy.linalg.eigh(T[:m, :m], driver="evd", check_finite=False)
+            th, Y = th[::-1], Y[:, ::-1]
+            resB = np.linalg.norm(T[m:m + b, m - b:m] @ Y[m - b:m, :], axis=0)
+            st["t_host"] += time.perf_counter() - t0
+            return th, Y, resB
+        Td = torch.from_numpy(np.ascontiguousarray(T[:m + b, :m])).to(dev)
+        thd, Yd = torch.linalg.eigh(Td[:m, :m])
+        thd, Yd = thd.flip(0), Yd.flip(1)
+        resB = torch.linalg.vector_norm(Td[m:m + b, m - b:m] @ Yd[m - b:m, :], dim=0)
+        th, resB = thd.cpu().numpy(), resB.cpu().numpy()
+        st["t_eigh_gpu"] = st.get("t_eigh_gpu", 0.0) + time.perf_counter() - t0
+        return th, Yd, resB
 
     for blk in range(max_blocks):
         j0 = cur - b
@@ -354,7 +376,7 @@ def krylov_eigenpairs(A, k, upper_bound, cut, lam_k, paired=False, tol=1e-12, bl
                 hard = np.argsort(-estA)[:min(16, kw)]
                 hard.sort()
                 Xh = torch.empty((N, len(hard)), dtype=torch.float64, device=dev)
-                ops.right_multiply(V[:, :m], Y[:, hard], Xh)
+                ops.right_multiply(V[:, :m], Y[:, torch.from_numpy(hard).to(dev)] if isinstance(Y, torch.Tensor) else Y[:, hard], Xh)
                 res_h = _true_residuals(A, Xh, ops, h, comm)
                 if verbose:
                     print("  [krylov]   true residual of the hardest pairs: %.3e" % res_h.max())
@@ -378,7 +400,8 @@ def krylov_eigenpairs(A, k, upper_bound, cut, lam_k, paired=False, tol=1e-12, bl
                 V[:, p:p + b].copy_(V[:, m:cur].clone())
                 V[:, :p].copy_(Xk)
                 del Xk
-                Cpl = T[m:cur, m - b:m] @ Y[m - b:m, :p]
+                Ylast = Y[m - b:m, :p].cpu().numpy() if isinstance(Y, torch.Tensor) else Y[m - b:m, :p]
+                Cpl = T[m:cur, m - b:m] @ Ylast
                 Tn = np.zeros_like(T)
                 Tn[:p, :p] = np.diag(th[:p])
                 Tn[p:p + b, :p] = Cpl

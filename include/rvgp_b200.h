@@ -236,6 +236,13 @@ int rvgp_geodesic_neighbourhoods(rvgp_handle_t h, const int32_t* indptr, const i
                                  int maxdeg, int32_t* seq, int32_t* counts, int32_t* flags, void* workspace,
                                  int64_t workspace_bytes);
 int64_t rvgp_geodesic_workspace_bytes(rvgp_handle_t h, int n, int K, int maxdeg);
+/* multi-GPU form: only the sources [src_begin, src_begin + src_count) (rows of the full-size seq / counts), no stale-tail pass;
+ * all-gather the rows, OR the flags, then call rvgp_geodesic_fix_stale once on the complete arrays (pyx:350 copies the stale
+ * tail of a short component from the PREVIOUS source's row). */
+int rvgp_geodesic_neighbourhoods_range(rvgp_handle_t h, const int32_t* indptr, const int32_t* indices, int n, int K,
+                                       int maxdeg, int src_begin, int src_count, int32_t* seq, int32_t* counts,
+                                       int32_t* flags, void* workspace, int64_t workspace_bytes);
+int rvgp_geodesic_fix_stale(rvgp_handle_t h, int n, int K, int32_t* seq, const int32_t* counts, const int32_t* flags);
 
 /* ---- K5/K6: tangent frames (ptu_dijkstra.pyx:396-434) and dimension statistic (geometry.py:83-97) ------ */
 int rvgp_tangent_frames(rvgp_handle_t h, const double* X, int n, int D, const int32_t* seq, int Kp1, int dcheck,
@@ -297,6 +304,14 @@ int rvgp_trsm_f64(rvgp_handle_t h, const double* L, int64_t ldl, int n, double* 
 int rvgp_add_diag_f64(rvgp_handle_t h, double* A, int64_t lda, int n, double v);
 int rvgp_logdiag_sum_f64(rvgp_handle_t h, const double* A, int64_t lda, int n, double* out);
 int rvgp_kdiag_f64(rvgp_handle_t h, const double* X, int64_t ldx, int64_t n, int k, const double* S, double* out);
+
+/* ---- K15b: one rank-k GP evaluation for k > 64 enqueued as a whole (build B = I + S^1/2 G S^1/2 / noise, Cholesky, three
+ * triangular solves, column norms, log-determinant): the L-BFGS-B loop of train_gp (main.py:87-95) then costs one small
+ * host->device copy (par = [S (k), noise]), this call and one device->host copy of out per evaluation.
+ * out (2 + 2k doubles): [not-SPD flag, sum log L_ii, z = B^-1 (S^1/2 b), qs_j = ||L^-1 (S^1/2 G) e_j||^2]. */
+int rvgp_gp_lowrank_eval_f64(rvgp_handle_t h, int k, const double* G, const double* b, const double* par, double* out,
+                             void* workspace, int64_t workspace_bytes);
+int64_t rvgp_gp_lowrank_eval_workspace_bytes(int k);
 
 /* ---- K16: fused rank-k GP evaluation for small k (<= 64), one CTA per problem (many time frames per launch; the
  * EEG-shaped workload of examples/eeg_example/eeg_utils.py:26-35,107-112).  Inputs per problem: G = Phi^T Phi (k x k),

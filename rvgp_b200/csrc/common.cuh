@@ -25,7 +25,6 @@ struct Handle {
     int mma_variant;              // tuning: pipeline / occupancy variant of the native-layout MMA SpMM
     int mma_prefetch;             // tuning: L2 prefetch distance (warp iterations) of the native-layout MMA SpMM
     int mma_stream_policy;        // tuning: bit0 = no-L1-allocate W loads, bit1 = no-L1-allocate Y stores (MMA SpMM)
-    int halo_fused;               // experiment (default 0): signal + wait + pull of the peer-memory halo exchange in ONE kernel
 };
 
 inline Handle* H(rvgp_handle_t h) { return reinterpret_cast<Handle*>(h); }

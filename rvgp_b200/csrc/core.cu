@@ -26,7 +26,6 @@ extern "C" int rvgp_create(int device, rvgp_handle_t* out) {
     h->mma_stream_policy = 7;
     h->mma_variant = 1;
     h->mma_prefetch = 1;
-    h->halo_fused = 0;   // unmeasured experiment (csrc/halo.cu: halo_sync_pull_kernel); RVGP_HALO_FUSED=1 opts in
     h->last_error[0] = 0;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete h; return RVGP_ERR_CUDA; }
@@ -61,6 +60,5 @@ extern "C" int rvgp_set_option(rvgp_handle_t hh, const char* key, int value) {
     if (strcmp(key, "mma_prefetch") == 0) { H(hh)->mma_prefetch = value; return RVGP_OK; }
     if (strcmp(key, "mma_gpw") == 0) { H(hh)->mma_gpw = value; return RVGP_OK; }
     if (strcmp(key, "mma_stream_policy") == 0) { H(hh)->mma_stream_policy = value; return RVGP_OK; }
-    if (strcmp(key, "halo_fused") == 0) { H(hh)->halo_fused = value; return RVGP_OK; }
     return set_error(H(hh), RVGP_ERR_BAD_ARG, "unknown option %s%s", key);
 }

@@ -72,7 +72,7 @@ __device__ __forceinline__ void remove_node(const Pool& P, unsigned short node) 
 __global__ void __launch_bounds__(128)
 geodesic_kernel(const int* __restrict__ indptr, const int* __restrict__ indices, int n, int K, int cap, int hcap,
                 unsigned char* __restrict__ ws, int64_t slab_bytes, int* __restrict__ seq, int* __restrict__ counts,
-                int* __restrict__ flags) {
+                int* __restrict__ flags, int src_begin, int src_end) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nthreads = gridDim.x * blockDim.x;
     const int Kp1 = K + 1;
@@ -98,7 +98,7 @@ geodesic_kernel(const int* __restrict__ indptr, const int* __restrict__ indices,
 
     unsigned short roots[64];   // roots_by_rank (pyx:573); ranks stay < log2(cap)
 
-    for (int src = tid; src < n; src += nthreads) {
+    for (int src = src_begin + tid; src < src_end; src += nthreads) {
         int count = 0;            // nodes in the pool
         unsigned short min_node = NIL;
         int scanned = 0;
@@ -250,21 +250,44 @@ extern "C" int64_t rvgp_geodesic_workspace_bytes(rvgp_handle_t hh, int n, int K,
 
 // seq: (n, K+1) int32 popped node ids in pop order; counts: (n) pops per source; flags: device int32
 // (bit0 short component seen, bit1 decrease_val would have fired, bit2 pool overflow) -- zeroed here.
-extern "C" int rvgp_geodesic_neighbourhoods(rvgp_handle_t hh, const int32_t* indptr, const int32_t* indices, int n, int K,
-                                            int maxdeg, int32_t* seq, int32_t* counts, int32_t* flags, void* workspace,
-                                            int64_t workspace_bytes) {
-    Handle* h = H(hh);
+// The _range form computes only the sources [src_begin, src_begin + src_count) (rows of the FULL-size seq / counts arrays) and
+// leaves the stale-tail pass to the caller: sources are independent, so a multi-GPU caller gives every rank a contiguous
+// range, all-gathers the rows and runs rvgp_geodesic_fix_stale once on the complete arrays (the stale tail of a short
+// component copies from the PREVIOUS source's row, pyx:350, hence needs them all).
+static int geodesic_run(Handle* h, const int32_t* indptr, const int32_t* indices, int n, int K, int maxdeg, int src_begin,
+                        int src_count, int32_t* seq, int32_t* counts, int32_t* flags, void* workspace, int64_t workspace_bytes) {
     RVGP_REQUIRE(h, n >= 1 && K >= 1 && K < 250, "geodesic: K must be in [1,250)");
     RVGP_REQUIRE(h, K < n, "Geodesic neighborhood size must be less than the total number of samples");
+    RVGP_REQUIRE(h, src_begin >= 0 && src_count >= 0 && src_begin + src_count <= n, "geodesic: source range outside [0, n)");
     int cap, hcap; int64_t slab;
     geodesic_dims(K, maxdeg, &cap, &hcap, &slab);
     const int nthreads = geodesic_threads(h, n, slab);
     if ((int64_t)nthreads * slab > workspace_bytes) return set_error(h, RVGP_ERR_CAPACITY, "geodesic: workspace too small%s%s");
     RVGP_CUDA_OK(h, cudaMemsetAsync(flags, 0, sizeof(int), h->stream));
+    if (src_count == 0) return RVGP_OK;
     geodesic_kernel<<<nthreads / 128, 128, 0, h->stream>>>(indptr, indices, n, K, cap, hcap, (unsigned char*)workspace, slab,
-                                                           seq, counts, flags);
+                                                           seq, counts, flags, src_begin, src_begin + src_count);
     RVGP_LAUNCH_OK(h, "geodesic_kernel");
+    return RVGP_OK;
+}
+
+extern "C" int rvgp_geodesic_fix_stale(rvgp_handle_t hh, int n, int K, int32_t* seq, const int32_t* counts, const int32_t* flags) {
+    Handle* h = H(hh);
     geodesic_fix_stale_kernel<<<1, 1, 0, h->stream>>>(n, K + 1, seq, counts, flags);
     RVGP_LAUNCH_OK(h, "geodesic_fix_stale_kernel");
     return RVGP_OK;
+}
+
+extern "C" int rvgp_geodesic_neighbourhoods_range(rvgp_handle_t hh, const int32_t* indptr, const int32_t* indices, int n, int K,
+                                                  int maxdeg, int src_begin, int src_count, int32_t* seq, int32_t* counts,
+                                                  int32_t* flags, void* workspace, int64_t workspace_bytes) {
+    return geodesic_run(H(hh), indptr, indices, n, K, maxdeg, src_begin, src_count, seq, counts, flags, workspace, workspace_bytes);
+}
+
+extern "C" int rvgp_geodesic_neighbourhoods(rvgp_handle_t hh, const int32_t* indptr, const int32_t* indices, int n, int K,
+                                            int maxdeg, int32_t* seq, int32_t* counts, int32_t* flags, void* workspace,
+                                            int64_t workspace_bytes) {
+    int rc = geodesic_run(H(hh), indptr, indices, n, K, maxdeg, 0, n, seq, counts, flags, workspace, workspace_bytes);
+    if (rc) return rc;
+    return rvgp_geodesic_fix_stale(hh, n, K, seq, counts, flags);
 }

@@ -218,3 +218,75 @@ extern "C" int rvgp_kdiag_f64(rvgp_handle_t hh, const double* X, int64_t ldx, in
     RVGP_LAUNCH_OK(h, "kdiag_kernel");
     return RVGP_OK;
 }
+
+// ---- K15b: one rank-k GP evaluation (k > 64) without host round trips ------------------------------------------------------
+// The 4-scalar L-BFGS-B loop of train_gp (main.py:87-95) evaluates the rank-k log marginal likelihood ~100 times per fit; each
+// evaluation is O(k^3) on resident k x k data, so its cost is launch / synchronisation overhead, not arithmetic.  This entry
+// point enqueues the WHOLE evaluation (build B = I + S^1/2 G S^1/2 / noise, Cholesky, three triangular solves, column norms,
+// log-determinant) and packs what the host needs into `out`; the caller then makes ONE device->host copy of 2 + 2k doubles.
+namespace rvgp {
+__global__ void gp_lowrank_build_kernel(int k, const double* __restrict__ G, const double* __restrict__ b,
+                                        const double* __restrict__ par, double* __restrict__ B, double* __restrict__ Q,
+                                        double* __restrict__ rhs) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)k * k) return;
+    const int i = (int)(idx / k), j = (int)(idx - (int64_t)i * k);
+    const double noise = par[k];
+    const double ri = sqrt(par[i]), rj = sqrt(par[j]);
+    const double g = G[idx];
+    B[idx] = ((i == j) ? 1.0 : 0.0) + ri * g * rj / noise;
+    Q[idx] = ri * g;
+    if (j == 0) rhs[i] = ri * b[i];
+}
+
+__global__ void gp_lowrank_pack_kernel(int k, const int* __restrict__ flag, const double* __restrict__ logdet_half,
+                                       const double* __restrict__ z, const double* __restrict__ qs, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) { out[0] = (double)(*flag & 1); out[1] = *logdet_half; }
+    if (i < k) { out[2 + i] = z[i]; out[2 + k + i] = qs[i]; }
+}
+}  // namespace rvgp
+
+extern "C" int64_t rvgp_coldot_workspace_bytes(int64_t nrows, int ncols);
+extern "C" int rvgp_coldot_f64(rvgp_handle_t hh, int64_t nrows, int ncols, const double* A, int64_t lda, const double* B,
+                               int64_t ldb, double* out, double* workspace);
+
+// G (k x k), b (k): resident Gram data of the fit (Phi^T Phi, Phi^T y).  par: [S (k), noise] on the device.
+// work: 2 k^2 + 3 k + 2 doubles + rvgp_gp_lowrank_eval_workspace_bytes(k) in total, laid out by this function.
+// out (2 + 2k doubles): [not-SPD flag, sum log L_ii, z = B^-1 (S^1/2 b), qs_j = || L^-1 (S^1/2 G) e_j ||^2].
+extern "C" int64_t rvgp_gp_lowrank_eval_workspace_bytes(int k) {
+    const int64_t dbl = 2 * (int64_t)k * k + 3 * (int64_t)k + 16 + 64 * (int64_t)k;
+    return dbl * (int64_t)sizeof(double) + rvgp_potrf_workspace_bytes(k) + rvgp_coldot_workspace_bytes(k, k) + 256;
+}
+
+extern "C" int rvgp_gp_lowrank_eval_f64(rvgp_handle_t hh, int k, const double* G, const double* b, const double* par,
+                                        double* out, void* workspace, int64_t workspace_bytes) {
+    Handle* h = H(hh);
+    RVGP_REQUIRE(h, k >= 1, "gp_lowrank_eval: k >= 1");
+    if (rvgp_gp_lowrank_eval_workspace_bytes(k) > workspace_bytes)
+        return set_error(h, RVGP_ERR_CAPACITY, "gp_lowrank_eval: workspace too small%s%s");
+    double* B = (double*)workspace;
+    double* Q = B + (int64_t)k * k;
+    double* rhs = Q + (int64_t)k * k;
+    double* qs = rhs + k;
+    double* logdet = qs + k;                       // 1 double (+ padding)
+    int32_t* flag = (int32_t*)(logdet + 8);
+    double* scratch = logdet + 16;                 // 64 * k doubles (rvgp_trsm_f64)
+    char* tail = (char*)(scratch + 64 * (int64_t)k);
+    tail = (char*)(((uintptr_t)tail + 255) / 256 * 256);
+    void* potrf_ws = tail;
+    const int64_t pwb = rvgp_potrf_workspace_bytes(k);
+    double* cd_ws = (double*)(tail + (pwb + 255) / 256 * 256);
+    gp_lowrank_build_kernel<<<cdiv((int64_t)k * k, 256), 256, 0, h->stream>>>(k, G, b, par, B, Q, rhs);
+    RVGP_LAUNCH_OK(h, "gp_lowrank_build_kernel");
+    int rc;
+    if ((rc = rvgp_potrf_f64(hh, B, k, k, flag, potrf_ws, pwb))) return rc;
+    if ((rc = rvgp_trsm_f64(hh, B, k, k, rhs, 1, 1, 0, potrf_ws, scratch))) return rc;
+    if ((rc = rvgp_trsm_f64(hh, B, k, k, rhs, 1, 1, 1, potrf_ws, scratch))) return rc;
+    if ((rc = rvgp_trsm_f64(hh, B, k, k, Q, k, k, 0, potrf_ws, scratch))) return rc;
+    if ((rc = rvgp_coldot_f64(hh, k, k, Q, k, Q, k, qs, cd_ws))) return rc;
+    if ((rc = rvgp_logdiag_sum_f64(hh, B, k, k, logdet))) return rc;
+    gp_lowrank_pack_kernel<<<cdiv(k, 256), 256, 0, h->stream>>>(k, flag, logdet, rhs, qs, out);
+    RVGP_LAUNCH_OK(h, "gp_lowrank_pack_kernel");
+    return RVGP_OK;
+}

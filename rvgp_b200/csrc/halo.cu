@@ -63,44 +63,6 @@ __global__ void halo_pull_kernel(int n_halo, int row_doubles, const int64_t* __r
     }
 }
 
-// Experiment (Handle::halo_fused, default off, NOT yet measured): the three small kernels of a step in one launch.  Block 0
-// signals first (its threads < n_peers), then EVERY block waits for the neighbours' flags on its own (no dependency between
-// the blocks of this kernel, so co-residency is not required; block 0 is scheduled first, so the signal is never stuck behind
-// the waits), then pulls its share of the halo rows.  At 8 GPUs a degree step is ~0.149 ms for ~0.11 ms of SpMM
-// (profiles/r01d_bench_c4_n8_paired.json); two launches fewer per step is what this buys.
-__global__ void __launch_bounds__(256)
-halo_sync_pull_kernel(unsigned long long* const* __restrict__ peer_slots, const unsigned long long* __restrict__ flags,
-                      const int* __restrict__ wait_idx, int n_peers, unsigned long long epoch, unsigned long long timeout_ns,
-                      int* __restrict__ err, int n_halo, int row_doubles, const int64_t* __restrict__ src, double* __restrict__ dst) {
-    const int t = threadIdx.x;
-    if (blockIdx.x == 0 && t < n_peers) {
-        __threadfence_system();
-        asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(peer_slots[t]), "l"(epoch) : "memory");
-    }
-    if (t < n_peers) {
-        const unsigned long long* f = flags + wait_idx[t];
-        const unsigned long long t0 = globaltimer_ns();
-        for (;;) {
-            unsigned long long v;
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
-            if (v >= epoch) break;
-            if (globaltimer_ns() - t0 > timeout_ns) { atomicOr(err, 1); break; }
-            __nanosleep(200);
-        }
-    }
-    __syncthreads();
-    const int lane = t & 31;
-    const int node = blockIdx.x * (blockDim.x >> 5) + (t >> 5);
-    if (node >= n_halo) return;
-    const double* s = reinterpret_cast<const double*>(src[node]);
-    double* d = dst + (int64_t)node * row_doubles;
-    for (int c = lane * 2; c < row_doubles; c += 64) {
-        double a, b;
-        asm volatile("ld.volatile.global.v2.f64 {%0,%1}, [%2];" : "=d"(a), "=d"(b) : "l"(s + c));
-        *reinterpret_cast<double2*>(d + c) = make_double2(a, b);
-    }
-}
-
 int spmm_dispatch_public(Handle* h, int nbrows, int d, const int* indptr, const int* indices, const double* vals,
                          const double* X, int64_t ldx, const double* W, int64_t ldw, double* Y, int64_t ldy, int ncols,
                          double alpha, double beta, double gamma);
@@ -132,21 +94,12 @@ static int halo_pull(Handle* h, const rvgp_halo_ctx* c, int slot) {
 static int halo_step(Handle* h, const rvgp_halo_ctx* c, unsigned long long epoch, int x, int w, int y, double alpha, double beta,
                      double gamma) {
     int rc;
-    if (h->halo_fused && c->n_peers > 0 && c->n_peers <= 32) {
-        const int row_doubles = c->d * c->ncols;
-        double* dst = c->E[x] + (int64_t)c->n_loc * row_doubles;
-        const int blocks = c->n_halo > 0 ? cdiv(c->n_halo, 8) : 1;      // a rank without halo rows still signals and waits
-        halo_sync_pull_kernel<<<blocks, 256, 0, h->stream>>>(
-            reinterpret_cast<unsigned long long* const*>(c->peer_slots), reinterpret_cast<const unsigned long long*>(c->flags),
-            c->wait_idx, c->n_peers, epoch, (unsigned long long)c->timeout_ms * 1000000ull, c->err, c->n_halo, row_doubles,
-            c->pull_src[x], dst);
-        RVGP_LAUNCH_OK(h, "halo_sync_pull_kernel");
-    } else {
-        rc = halo_sync(h, c, epoch);
-        if (rc) return rc;
-        rc = halo_pull(h, c, x);
-        if (rc) return rc;
-    }
+    // (a single signal + wait + pull kernel was tried in round 2: on 2 B200s it was SLOWER and erratic -- every block of the
+    // pull grid spins on the flags while occupying an SM -- so the three small kernels stay; profiles/r02g_*)
+    rc = halo_sync(h, c, epoch);
+    if (rc) return rc;
+    rc = halo_pull(h, c, x);
+    if (rc) return rc;
     const double* W = (w >= 0) ? c->E[w] : nullptr;
     if (c->kptr != nullptr && c->rotc == 2) {
         // scalar pattern-mode Laplacian as L (x) I_2: the row-major extended buffers ARE native panels with ncols / 2 columns

@@ -183,7 +183,11 @@ class data:
         if K < D:
             raise ValueError("Geodesic neighborhood size must be larger or equal to the embedding dimension")
         max_row = graph.max_row
-        seq, _ = geo.geodesic_neighbourhoods_device(graph.indptr, graph.indices, int(K), max_row)
+        geo_comm = None
+        if shard:
+            from .distributed import Comm
+            geo_comm = Comm()
+        seq, _ = geo.geodesic_neighbourhoods_device(graph.indptr, graph.indices, int(K), max_row, comm=geo_comm)
         self.timings["geodesic"] = tick() - t0
         stage('tangent_frames')
         t0 = tick()

@@ -175,9 +175,6 @@ class PeerHalo:
         dev = op.indptr.device
         self.h = h = get_handle(dev.index)
         lib = h.lib
-        import os
-        if os.environ.get("RVGP_HALO_FUSED") == "1":        # unmeasured experiment: one kernel for signal + wait + pull (csrc/halo.cu)
-            h.set_option("halo_fused", 1)
         world, rank, group = plan.world, plan.rank, plan.group
         row_bytes = d * self.ncols * 8
         ebytes = max(256, (plan.n_loc + plan.n_halo) * row_bytes)

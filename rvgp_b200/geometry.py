@@ -85,8 +85,9 @@ def knn_to_csr_device(knn):
     return indptr, indices[:nnz].clone()
 
 
-def geodesic_neighbourhoods_device(indptr, indices, K, maxrow=None):
-    """K4.  Returns seq (n, K+1) int32 in the reference heap's pop order, counts (n)."""
+def geodesic_neighbourhoods_device(indptr, indices, K, maxrow=None, comm=None):
+    """K4.  Returns seq (n, K+1) int32 in the reference heap's pop order, counts (n).  ``comm`` (distributed.Comm, world > 1):
+    the sources are independent, so every rank runs a contiguous range and the rows are all-gathered."""
     h = get_handle(indptr.device.index)
     n = indptr.numel() - 1
     K = int(K)
@@ -99,7 +100,20 @@ def geodesic_neighbourhoods_device(indptr, indices, K, maxrow=None):
     seq = torch.zeros((n, K + 1), dtype=torch.int32, device=indptr.device)
     counts = torch.empty(n, dtype=torch.int32, device=indptr.device)
     flags = torch.zeros(1, dtype=torch.int32, device=indptr.device)
-    h.call("rvgp_geodesic_neighbourhoods", indptr, indices, int(n), K, int(maxrow), seq, counts, flags, ws, I64(wsb))
+    if comm is not None and comm.world > 1:
+        s0, s1 = (n * comm.rank) // comm.world, (n * (comm.rank + 1)) // comm.world
+        h.call("rvgp_geodesic_neighbourhoods_range", indptr, indices, int(n), K, int(maxrow), int(s0), int(s1 - s0), seq, counts,
+               flags, ws, I64(wsb))
+        rows = [(n * (r + 1)) // comm.world - (n * r) // comm.world for r in range(comm.world)]
+        both = torch.cat([seq[s0:s1], counts[s0:s1, None]], dim=1)
+        both = comm.allgather_rows(both, rows)
+        seq, counts = both[:, :K + 1].contiguous(), both[:, K + 1].contiguous()
+        bits = torch.stack([(flags >> i) & 1 for i in range(3)]).reshape(3).to(torch.int32)      # OR over the ranks, bit by bit
+        comm.allreduce_(bits)
+        flags = ((bits[0] > 0).to(torch.int32) | ((bits[1] > 0).to(torch.int32) << 1) | ((bits[2] > 0).to(torch.int32) << 2)).reshape(1)
+        h.call("rvgp_geodesic_fix_stale", int(n), K, seq, counts, flags)
+    else:
+        h.call("rvgp_geodesic_neighbourhoods", indptr, indices, int(n), K, int(maxrow), seq, counts, flags, ws, I64(wsb))
     f = int(flags.item())
     if f & 2:
         raise RvgpError(-1, "geodesic: decrease_val would fire (non-unit weights are not supported)")

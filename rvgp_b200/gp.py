@@ -101,6 +101,17 @@ class DeviceGPR:
         Gh = 0.5 * (Gh + Gh.T)
         self.G, self.b, self.yy = Gh[:k, :k].copy(), Gh[:k, k].copy(), float(Gh[k, k])
         self._small = k <= 64
+        if not self._small:
+            # K15b: the whole evaluation is one C call on resident data (rvgp_gp_lowrank_eval_f64); per evaluation the host
+            # uploads k + 1 doubles and reads back 2 + 2k
+            self._Gd = _f64(self.G, self.dev)
+            self._bd = _f64(self.b, self.dev)
+            self._par_h = torch.empty(k + 1, dtype=torch.float64).pin_memory()
+            self._par_d = torch.empty(k + 1, dtype=torch.float64, device=self.dev)
+            self._out_h = torch.empty(2 + 2 * k, dtype=torch.float64).pin_memory()
+            self._out_d = torch.empty(2 + 2 * k, dtype=torch.float64, device=self.dev)
+            self._ev_wsb = int(self.h.query("rvgp_gp_lowrank_eval_workspace_bytes", int(k)))
+            self._ev_ws = torch.empty(self._ev_wsb, dtype=torch.uint8, device=self.dev)
         if self._small:
             # K16: everything an evaluation needs stays resident; one fused launch per evaluation
             self._Gd = _f64(self.G, self.dev)
@@ -143,29 +154,28 @@ class DeviceGPR:
             if not np.isfinite(o[0]):
                 raise RvgpError(RVGP_ERR_NOT_SPD, "Cholesky decomposition was not successful. The input might not be valid.")
             return (float(o[0]), o[2:2 + k].copy(), float(o[1])) if grads else float(o[0])
-        rs, ch = self._lowrank_factor(S, noise)
+        rs = np.sqrt(S)
         bt = rs * self.b
-        rhs = _f64(bt.reshape(k, 1), self.dev)
-        ch.solve(rhs, 0)
-        ch.solve(rhs, 1)
-        logdet_half = ch.logdiag_sum()
-        if grads:
-            Q = _f64(rs[:, None] * self.G, self.dev)
-            ch.solve(Q, 0)
-            qs = torch.empty(k, dtype=torch.float64, device=self.dev)
-            ws = torch.empty(max(1, self.h.query("rvgp_coldot_workspace_bytes", I64(k), int(k)) // 8),
-                             dtype=torch.float64, device=self.dev)
-            self.h.call("rvgp_coldot_f64", I64(k), int(k), Q, I64(Q.stride(0)), Q, I64(Q.stride(0)), qs, ws)
-        ch.check()
-        z = rhs.cpu().numpy()[:, 0]
+        self._par_h[:k] = torch.from_numpy(np.ascontiguousarray(S))
+        self._par_h[k] = noise
+        self._par_d.copy_(self._par_h, non_blocking=True)
+        self.h.sync_stream()
+        self.h.call("rvgp_gp_lowrank_eval_f64", int(k), self._Gd, self._bd, self._par_d, self._out_d, self._ev_ws, I64(self._ev_wsb))
+        self._out_h.copy_(self._out_d)                          # the one synchronising read-back of the evaluation
+        o = self._out_h.numpy()
+        if o[0] != 0.0 or not np.isfinite(o[1]):
+            raise RvgpError(RVGP_ERR_NOT_SPD, "Cholesky decomposition was not successful. The input might not be valid.")
+        logdet_half = float(o[1])
+        z = o[2:2 + k].copy()
+        qs_h = o[2 + k:2 + 2 * k].copy()
         quad = (self.yy - (bt @ z) / noise) / noise
-        lml = float(-0.5 * quad - 0.5 * M * LOG2PI - 0.5 * M * math.log(noise) - float(logdet_half.item()))
+        lml = float(-0.5 * quad - 0.5 * M * LOG2PI - 0.5 * M * math.log(noise) - logdet_half)
         if not grads:
             return lml
         c = rs * z
         Gc = self.G @ c
         u = (self.b - Gc / noise) / noise
-        wdiag = (np.diag(self.G) - qs.cpu().numpy() / noise) / noise
+        wdiag = (np.diag(self.G) - qs_h / noise) / noise
         dS = 0.5 * u ** 2 - 0.5 * wdiag
         aa = (self.yy - 2.0 * (self.b @ c) / noise + (c @ Gc) / noise ** 2) / noise ** 2
         tr_inv = (M - (S * wdiag).sum()) / noise

@@ -257,6 +257,7 @@ def krylov_eigenpairs(A, k, upper_bound, cut, lam_k, paired=False, tol=1e-12, bl
     w2 = torch.empty((N, b), dtype=torch.float64, device=dev) if (isinstance(A, BsrMatrix) and A.mma is not None and A.d == 2) else None
     Wb = torch.empty((N, b), dtype=torch.float64, device=dev)             # the block being filtered (contiguous panel)
     st["spmm_kernel"] = "mma_native" if w2 is not None else ("mma_native_pattern" if getattr(A, "mma_pattern", None) is not None else "gather")
+    sharded_name = not isinstance(A, BsrMatrix) and hasattr(A, "spmm_kernel_name")
     ops = FieldOps(h, N, cap, b, dev, comm, paired)
     cdt = np.complex128 if paired else np.float64
     T = np.zeros((cap, cap), dtype=cdt)
@@ -412,6 +413,8 @@ def krylov_eigenpairs(A, k, upper_bound, cut, lam_k, paired=False, tol=1e-12, bl
                 st["restarts"] += 1
     st["outer"] = st["blocks"]
     st["dense_tflop"] = ops.flops / 1e12
+    if sharded_name:
+        st["spmm_kernel"] = A.spmm_kernel_name
     if retry_cut is not None:
         del V, w0, w1, w2, Wb, ops
         prev = dict(st)
@@ -452,6 +455,8 @@ def krylov_eigenpairs(A, k, upper_bound, cut, lam_k, paired=False, tol=1e-12, bl
     st["m_final"] = st2.get("m")
     st["residual_max"], st["converged"], st["tol_abs"] = st2["residual_max"], st2["converged"], st2["tol_abs"]
     st["cholqr_passes"] = st2.get("cholqr_passes", 0)
+    if sharded_name:
+        st["spmm_kernel"] = A.spmm_kernel_name
     return evals, evecs
 
 

@@ -214,3 +214,39 @@ def test_full_decomposition_when_n_eigenpairs_is_none():
     np.testing.assert_allclose(d.evals_L, evL, rtol=1e-9, atol=1e-10)
     d2 = data(X, n_eigenpairs=250, verbose=False)            # k close to N
     np.testing.assert_allclose(d2.evals_L, evL[:250], rtol=1e-8, atol=1e-9)
+
+
+def test_geodesic_source_ranges_equal_full_run():
+    """Multi-GPU form of K4 (rvgp_geodesic_neighbourhoods_range + rvgp_geodesic_fix_stale): sources are independent, so
+    computing them in contiguous ranges and running the stale-tail pass once on the assembled arrays reproduces the
+    single call bit for bit -- including the reference's stale-tail quirk across a range boundary (pyx:350)."""
+    from rvgp_b200 import geometry as geo
+    from rvgp_b200._cabi import get_handle, I64
+    from oracle import rvgp_oracle as O
+    rng = np.random.default_rng(0)
+    X = np.concatenate([rng.normal(size=(40, 3)), rng.normal(size=(12, 3)) + 100, rng.normal(size=(13, 3)) - 100,
+                        rng.normal(size=(300, 3)) * 3 + 30])
+    ip, ix = O.symmetrize_csr(O.knn_exact(X, 10))
+    n, K = len(X), 15
+    ipd, ixd = _t(ip), _t(ix)
+    seq_full, cnt_full = geo.geodesic_neighbourhoods_device(ipd, ixd, K)
+    seq_ref, cnt_ref = O.geodesic_neighbourhoods(ip, ix, K)
+    assert np.array_equal(seq_full.cpu().numpy(), seq_ref) and cnt_ref.min() < K + 1
+    h = get_handle(0)
+    maxrow = int(np.diff(ip).max())
+    wsb = h.query("rvgp_geodesic_workspace_bytes", h._h, int(n), K, maxrow)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=_dev())
+    seq = torch.zeros((n, K + 1), dtype=torch.int32, device=_dev())
+    cnt = torch.zeros(n, dtype=torch.int32, device=_dev())
+    allflags = 0
+    for s0, s1 in ((0, 45), (45, 46), (46, 46), (46, n)):          # boundaries inside the short components, an empty range
+        fl = torch.zeros(1, dtype=torch.int32, device=_dev())
+        h.call("rvgp_geodesic_neighbourhoods_range", ipd, ixd, int(n), K, maxrow, int(s0), int(s1 - s0), seq, cnt, fl, ws, I64(wsb))
+        allflags |= int(fl.item())
+    assert allflags & 1
+    fl = torch.tensor([allflags], dtype=torch.int32, device=_dev())
+    h.call("rvgp_geodesic_fix_stale", int(n), K, seq, cnt, fl)
+    assert np.array_equal(cnt.cpu().numpy(), cnt_ref)
+    assert np.array_equal(seq.cpu().numpy(), seq_ref)
+    with pytest.raises(ValueError):
+        h.call("rvgp_geodesic_neighbourhoods_range", ipd, ixd, int(n), K, maxrow, int(n - 3), 10, seq, cnt, fl, ws, I64(wsb))

@@ -32,20 +32,23 @@ def main():
             rs = np.random.RandomState(0)
             train_ind = rs.choice(np.arange(n), size=n // 2)
             test_ind = np.setdiff1d(np.arange(n), train_ind)
-            outs = []
-            for dd in (d, d1):
-                dd.vectors = g["smoothed_field"]
-                P.set_default_positive_minimum(0.0)
-                with contextlib.redirect_stdout(io.StringIO()):
-                    gp = RVGP.fit(dd, train_ind=train_ind, noise_variance=0.001, solver="lowrank")
-                m, v = gp.transform(dd, test_ind)
-                outs.append((m, v, gp.l2_error, [float(p.value) for p in gp.trainable_parameters], getattr(gp, "comm", None) is not None))
-            dm = np.abs(outs[0][0] - outs[1][0]).max() / np.abs(outs[1][0]).max()
-            dv = np.abs(outs[0][1] - outs[1][1]).max() / np.abs(outs[1][1]).max()
-            if rank == 0:
-                print("GP sharded (comm=%s) vs replicated (comm=%s): mean rel %.2e  var rel %.2e  l2 %.6f / %.6f  params %s" %
-                      (outs[0][4], outs[1][4], dm, dv, outs[0][2], outs[1][2], np.round(outs[0][3], 6)))
-            ok = ok and outs[0][4] and not outs[1][4] and dm < 1e-6 and dv < 1e-6 and abs(outs[0][2] - outs[1][2]) < 1e-8
+            for epochs, tol in ((0, 1e-9), (1000, 1e-3)):
+                # epochs = 0: FIXED hyper-parameters, the two paths must agree to rounding; epochs = 1000: the L-BFGS-B
+                # trajectories see Gram matrices that differ in the last bit (summation order), so only the fit quality is compared
+                outs = []
+                for dd in (d, d1):
+                    dd.vectors = g["smoothed_field"]
+                    P.set_default_positive_minimum(0.0)
+                    with contextlib.redirect_stdout(io.StringIO()):
+                        gp = RVGP.fit(dd, train_ind=train_ind, noise_variance=0.001, solver="lowrank", epochs=epochs)
+                    m, v = gp.transform(dd, test_ind)
+                    outs.append((m, v, gp.l2_error, getattr(gp, "comm", None) is not None))
+                dm = np.abs(outs[0][0] - outs[1][0]).max() / np.abs(outs[1][0]).max()
+                dv = np.abs(outs[0][1] - outs[1][1]).max() / np.abs(outs[1][1]).max()
+                if rank == 0:
+                    print("GP epochs=%d sharded (comm=%s) vs replicated (comm=%s): mean rel %.2e  var rel %.2e  l2 %.8f / %.8f" %
+                          (epochs, outs[0][3], outs[1][3], dm, dv, outs[0][2], outs[1][2]))
+                ok = ok and outs[0][3] and not outs[1][3] and dm < tol and dv < tol and abs(outs[0][2] - outs[1][2]) < tol
     # timing at C2 scale
     from tests.workloads import make_cloud
     X = make_cloud("torus", int(os.environ.get("DIST_N", "200000")), 0)

@@ -23,6 +23,7 @@ struct Handle {
     int dgemm_dmma;               // tuning: FP64 tensor (mma.sync m8n8k4) instead of the DFMA register tile
     int mma_gpw;                  // tuning: row groups per warp in the MMA SpMM (0 = default)
     int mma_variant;              // tuning: pipeline / occupancy variant of the native-layout MMA SpMM
+    int mma_variant_n2;           // tuning: the same for panels of 32 native columns (2 chunks)
     int mma_prefetch;             // tuning: L2 prefetch distance (warp iterations) of the native-layout MMA SpMM
     int mma_stream_policy;        // tuning: bit0 = no-L1-allocate W loads, bit1 = no-L1-allocate Y stores (MMA SpMM)
 };

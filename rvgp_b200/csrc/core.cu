@@ -25,6 +25,7 @@ extern "C" int rvgp_create(int device, rvgp_handle_t* out) {
     // of 2 k-steps, persistent warp-strided schedule, streams evict-first in L2, L2 prefetch one group ahead
     h->mma_stream_policy = 7;
     h->mma_variant = 1;
+    h->mma_variant_n2 = 1;   // (2 chunks, ring 2, 256 threads x 3 CTAs/SM): 0.423 vs 0.448 ms for the 64-column L panels (profiles/r02_k9_sweep.txt)
     h->mma_prefetch = 1;
     h->last_error[0] = 0;
     cudaDeviceProp prop;
@@ -57,6 +58,7 @@ extern "C" int rvgp_set_option(rvgp_handle_t hh, const char* key, int value) {
     if (strcmp(key, "spmm_stage") == 0) { H(hh)->spmm_stage = value; return RVGP_OK; }
     if (strcmp(key, "dgemm_dmma") == 0) { H(hh)->dgemm_dmma = value; return RVGP_OK; }
     if (strcmp(key, "mma_variant") == 0) { H(hh)->mma_variant = value; return RVGP_OK; }
+    if (strcmp(key, "mma_variant_n2") == 0) { H(hh)->mma_variant_n2 = value; return RVGP_OK; }
     if (strcmp(key, "mma_prefetch") == 0) { H(hh)->mma_prefetch = value; return RVGP_OK; }
     if (strcmp(key, "mma_gpw") == 0) { H(hh)->mma_gpw = value; return RVGP_OK; }
     if (strcmp(key, "mma_stream_policy") == 0) { H(hh)->mma_stream_policy = value; return RVGP_OK; }

@@ -532,7 +532,12 @@ int spmm_mma_native_dispatch(Handle* h, int nbrows, const int* kptr, const int* 
         if (var == 0) RVGP_MMAN(4, 2, 128, 4); else if (var == 2) RVGP_MMAN(4, 3, 128, 4); else if (var == 3) RVGP_MMAN(4, 3, 256, 2);
         else if (var == 5) RVGP_MMAN(4, 4, 128, 3); else if (var == 6) RVGP_MMAN(4, 3, 384, 1); else RVGP_MMAN(4, 2, 256, 2);
     } else if (nch == 2) {
-        RVGP_MMAN(2, 2, 128, 6);
+        // 32 native columns = the 64-column row-major panels of the scalar Laplacian (AMODE 2) in the Krylov solver.
+        // (chunks, ring depth, threads, CTAs/SM) swept with tools/profile_k9.py, profiles/r02_k9_sweep.txt
+        const int v2 = h->mma_variant_n2;
+        if (v2 == 1) RVGP_MMAN(2, 2, 256, 3); else if (v2 == 2) RVGP_MMAN(2, 3, 128, 6); else if (v2 == 3) RVGP_MMAN(2, 4, 128, 4);
+        else if (v2 == 4) RVGP_MMAN(2, 3, 256, 3); else if (v2 == 5) RVGP_MMAN(2, 4, 256, 2); else if (v2 == 6) RVGP_MMAN(2, 4, 128, 6);
+        else RVGP_MMAN(2, 2, 128, 6);
     } else {
         RVGP_MMAN(1, 2, 128, 6);
     }

@@ -164,6 +164,7 @@ def run_b200(args):
         torch.cuda.synchronize(dev)
 
     mem_trace = []
+    step_wall = []
 
     def timed(fn, steps):
         """EXACTLY `steps` steps between two device events, barrier + synchronize on both sides, max over ranks.  Only the
@@ -172,12 +173,16 @@ def run_b200(args):
         barrier()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
+        tprev = time.perf_counter()
         for _ in range(steps):
             last = None                               # drop the previous step's outputs before the next one allocates
             summ, mean, var = fn()
             summs.append(summ)
             last = (mean, var)
             mem_trace.append(int(torch.cuda.memory_allocated(dev)))
+            tnow = time.perf_counter()
+            step_wall.append(round(tnow - tprev, 4))
+            tprev = tnow
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -244,6 +249,7 @@ def run_b200(args):
                                 "achieved": round(stL["spmm_bytes_fused"] / tL / 1e9, 1),
                                 "frac": round(stL["spmm_bytes_fused"] / tL / 1e9 / peak, 4)}
     mem_timed = list(mem_trace)
+    step_wall_timed = list(step_wall)
     # e2e: host buffers in / out through the public API
     gc.collect()
     n_e2e = max(1, min(args.steps, 2))
@@ -272,6 +278,7 @@ def run_b200(args):
         "eig_L": {a: _rnd(b) for a, b in stL.items()},
         "paired": bool(s_last["stats"].get("paired", False)),
         "gp": s_last["gp"],
+        "step_wall_s": step_wall_timed,
         "hbm_allocated_after_step_gb": {"first": round(mem_timed[0] / 1e9, 2), "last": round(mem_timed[-1] / 1e9, 2),
                                         "max": round(max(mem_timed) / 1e9, 2),
                                         "peak_gb": round(torch.cuda.max_memory_allocated(dev) / 1e9, 2)},
@@ -284,6 +291,8 @@ def run_b200(args):
                 res["cpu_baseline"] = {"value": None, "unit": "s", "cores": 1, "kind": "port", "sample": "failed: %r" % (e,)}
         _emit(res)
     if world > 1:
+        from rvgp_b200.distributed import release_ipc_pool
+        release_ipc_pool()                              # collective: unmap the pooled CUDA-IPC halo buffers, then free them
         dist.destroy_process_group()
 
 

@@ -149,7 +149,11 @@ typedef struct rvgp_halo_ctx {
     const int32_t* wait_idx;
     int32_t* err;
     int32_t timeout_ms;
-    int32_t reserved;
+    int32_t n_interior;             /* MMA plans only: row groups (4 block rows) that read local rows only ... */
+    const int32_t* glist_interior;
+    const int32_t* glist_boundary;  /* ... and those that also read halo rows.  Both NULL: one launch over all groups after the */
+    int32_t n_boundary;             /* exchange.  Given: signal -> interior groups -> wait -> pull -> boundary groups, i.e. the */
+    int32_t reserved;               /* neighbours' skew and the pull hide behind the interior launch. */
 } rvgp_halo_ctx;
 int rvgp_ipc_alloc(rvgp_handle_t h, int64_t bytes, void** dptr, uint8_t* handle64);
 int rvgp_ipc_open(rvgp_handle_t h, const uint8_t* handle64, void** dptr);

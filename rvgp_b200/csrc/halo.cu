@@ -69,6 +69,9 @@ int spmm_dispatch_public(Handle* h, int nbrows, int d, const int* indptr, const 
 int spmm_mma_native_dispatch(Handle* h, int nbrows, const int* kptr, const int* kcols, const double* afrag, int rotc,
                              const double* X, int64_t nsx, const double* W, int64_t nsw, double* Y, int64_t nsy,
                              int ncols, double alpha, double beta, double gamma, int reverse);
+int spmm_mma_native_dispatch_list(Handle* h, int nbrows, const int* kptr, const int* kcols, const double* afrag, int rotc,
+                                  const double* X, int64_t nsx, const double* W, int64_t nsw, double* Y, int64_t nsy,
+                                  int ncols, double alpha, double beta, double gamma, int reverse, const int* glist, int nlist);
 int native_convert(Handle* h, bool to_native, int nbrows, int ncols, double* V, int64_t ldv, double* Xn, int64_t ns);
 
 static int halo_sync(Handle* h, const rvgp_halo_ctx* c, unsigned long long epoch) {
@@ -94,13 +97,39 @@ static int halo_pull(Handle* h, const rvgp_halo_ctx* c, int slot) {
 static int halo_step(Handle* h, const rvgp_halo_ctx* c, unsigned long long epoch, int x, int w, int y, double alpha, double beta,
                      double gamma) {
     int rc;
+    const double* W = (w >= 0) ? c->E[w] : nullptr;
+    if (c->kptr != nullptr && c->glist_interior != nullptr && c->glist_boundary != nullptr) {
+        // Overlapped order (MMA plans with interior / boundary group lists).  The neighbours only ever pull my BOUNDARY rows (the
+        // pattern is symmetric: a row they need is a row of mine that references one of theirs), so the interior groups of this
+        // step may run -- and overwrite interior rows of E[y] -- before anybody has been waited for; the boundary groups keep the
+        // three-buffer guarantee (they are written after the wait).  By the time the interior launch (most of the rows) is done
+        // the neighbours have long signalled: their skew and the pull cost nothing.
+        const int rotc = c->rotc;
+        const int64_t ns = (rotc == 2) ? (int64_t)c->ncols : 2 * (int64_t)c->ncols;
+        const int ncn = (rotc == 2) ? c->ncols / 2 : c->ncols;
+        if (c->n_peers > 0) {
+            halo_signal_kernel<<<1, 32, 0, h->stream>>>(reinterpret_cast<unsigned long long* const*>(c->peer_slots), c->n_peers, epoch);
+            RVGP_LAUNCH_OK(h, "halo_signal_kernel");
+        }
+        rc = spmm_mma_native_dispatch_list(h, c->n_loc, c->kptr, c->kcols, c->afrag, rotc, c->E[x], ns, W, ns, c->E[y], ns, ncn, alpha,
+                                           beta, gamma, 0, c->glist_interior, c->n_interior);
+        if (rc) return rc;
+        if (c->n_peers > 0) {
+            halo_wait_kernel<<<1, 32, 0, h->stream>>>(reinterpret_cast<const unsigned long long*>(c->flags), c->wait_idx, c->n_peers,
+                                                      epoch, (unsigned long long)c->timeout_ms * 1000000ull, c->err);
+            RVGP_LAUNCH_OK(h, "halo_wait_kernel");
+        }
+        rc = halo_pull(h, c, x);
+        if (rc) return rc;
+        return spmm_mma_native_dispatch_list(h, c->n_loc, c->kptr, c->kcols, c->afrag, rotc, c->E[x], ns, W, ns, c->E[y], ns, ncn, alpha,
+                                             beta, gamma, 0, c->glist_boundary, c->n_boundary);
+    }
     // (a single signal + wait + pull kernel was tried in round 2: on 2 B200s it was SLOWER and erratic -- every block of the
     // pull grid spins on the flags while occupying an SM -- so the three small kernels stay; profiles/r02g_*)
     rc = halo_sync(h, c, epoch);
     if (rc) return rc;
     rc = halo_pull(h, c, x);
     if (rc) return rc;
-    const double* W = (w >= 0) ? c->E[w] : nullptr;
     if (c->kptr != nullptr && c->rotc == 2) {
         // scalar pattern-mode Laplacian as L (x) I_2: the row-major extended buffers ARE native panels with ncols / 2 columns
         const int64_t ns = (int64_t)c->ncols;

@@ -273,7 +273,7 @@ bsr_spmm_mma_native_kernel(int ngroups, int nbrows, const int* __restrict__ kptr
                            const double* __restrict__ afrag, const double* __restrict__ X, int64_t nsx,
                            const double* __restrict__ W, int64_t nsw, double* __restrict__ Y, int64_t nsy, double ascale,
                            double afold, double yscale, int has_w, int groups_per_warp, int persistent, int pdist,
-                           int policy, int reverse) {
+                           int policy, int reverse, const int* __restrict__ glist) {
     constexpr int NW = NT / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int kq = lane & 3, nn = lane >> 2;
@@ -320,8 +320,11 @@ bsr_spmm_mma_native_kernel(int ngroups, int nbrows, const int* __restrict__ kptr
         return fma(ascale, v, ((cw & (int)(0x80000000u | (unsigned)colmask)) == own) ? afold : 0.0);
     };
 
-    int g = gstart;
-    for (int it = 0; it < niter && g < ngroups; ++it, g += gstep) {
+    // glist != NULL: `ngroups` is the length of a LIST of row groups to process (row-sharded runs split the groups into those
+    // that only read local rows and those that also read halo rows, so the interior launch can overlap the halo exchange)
+    int gi = gstart;
+    for (int it = 0; it < niter && gi < ngroups; ++it, gi += gstep) {
+        const int g = glist ? __ldg(glist + gi) : gi;
         const int s0 = __ldg(kptr + g), s1 = __ldg(kptr + g + 1);
         const int own = (q == p) ? (g * 4 + r) : -1;      // column whose A entry takes the folded beta
         const int node = g * 4 + r;
@@ -329,8 +332,9 @@ bsr_spmm_mma_native_kernel(int ngroups, int nbrows, const int* __restrict__ kptr
         // L2 prefetch of what the warp's group `pdist` iterations ahead will stream from DRAM (its A fragments and W rows,
         // optionally its own X rows).  ncu showed the k-loop waiting a full DRAM latency per k-step (one k-step of
         // register prefetch, < 20 warps per SM); this turns those into L2 hits without holding registers.
-        const int gp = g + gstep * pdist;
-        const bool pf = pdist > 0 && it + pdist < niter && gp < ngroups;
+        const int gpi = gi + gstep * pdist;
+        const bool pf = pdist > 0 && it + pdist < niter && gpi < ngroups;
+        const int gp = pf ? (glist ? __ldg(glist + gpi) : gpi) : 0;
         int ps0 = 0, ps1 = 0;
         if (pf) { ps0 = __ldg(kptr + gp); ps1 = __ldg(kptr + gp + 1); }
         double acc[NCH][2][2];
@@ -493,9 +497,21 @@ int native_convert(Handle* h, bool to_native, int nbrows, int ncols, double* V, 
     return RVGP_OK;
 }
 
+int spmm_mma_native_dispatch_list(Handle* h, int nbrows, const int* kptr, const int* kcols, const double* afrag, int rotc,
+                                  const double* X, int64_t nsx, const double* W, int64_t nsw, double* Y, int64_t nsy,
+                                  int ncols, double alpha, double beta, double gamma, int reverse, const int* glist, int nlist);
+
 int spmm_mma_native_dispatch(Handle* h, int nbrows, const int* kptr, const int* kcols, const double* afrag, int rotc,
                              const double* X, int64_t nsx, const double* W, int64_t nsw, double* Y, int64_t nsy,
                              int ncols, double alpha, double beta, double gamma, int reverse) {
+    return spmm_mma_native_dispatch_list(h, nbrows, kptr, kcols, afrag, rotc, X, nsx, W, nsw, Y, nsy, ncols, alpha, beta, gamma,
+                                         reverse, nullptr, 0);
+}
+
+// glist (nullable, device int32[nlist]): process only these row groups (groups of 4 block rows), in list order.
+int spmm_mma_native_dispatch_list(Handle* h, int nbrows, const int* kptr, const int* kcols, const double* afrag, int rotc,
+                                  const double* X, int64_t nsx, const double* W, int64_t nsw, double* Y, int64_t nsy,
+                                  int ncols, double alpha, double beta, double gamma, int reverse, const int* glist, int nlist) {
     RVGP_REQUIRE(h, ncols >= 16 && ncols % 16 == 0, "spmm_mma_native: ncols must be a multiple of 16");
     RVGP_REQUIRE(h, nsx % 2 == 0 && nsy % 2 == 0 && (W == nullptr || nsw % 2 == 0) && (uintptr_t)X % 16 == 0 &&
                         (uintptr_t)Y % 16 == 0 && (uintptr_t)W % 16 == 0,
@@ -503,8 +519,8 @@ int spmm_mma_native_dispatch(Handle* h, int nbrows, const int* kptr, const int* 
     RVGP_REQUIRE(h, gamma == 0.0 || W != nullptr, "spmm_mma_native: W required when gamma != 0");
     RVGP_REQUIRE(h, Y != X && Y != W, "spmm_mma_native: Y must not alias X or W");
     RVGP_REQUIRE(h, alpha != 0.0, "spmm_mma_native: alpha must be non-zero (beta is folded into the matrix as beta / alpha)");
-    if (nbrows == 0) return RVGP_OK;
-    const int ngroups = cdiv(nbrows, 4);
+    if (nbrows == 0 || (glist != nullptr && nlist == 0)) return RVGP_OK;
+    const int ngroups = glist ? nlist : cdiv(nbrows, 4);
     const int gpw = h->mma_gpw;                       // 0 = persistent warp-strided schedule
     const int var = h->mma_variant;
     const int nch = (ncols % 64 == 0) ? 4 : ((ncols % 32 == 0) ? 2 : 1);
@@ -518,13 +534,13 @@ int spmm_mma_native_dispatch(Handle* h, int nbrows, const int* kptr, const int* 
         dim3 grid(gx, nslab);                                                                                          \
         if (rotc == 2) bsr_spmm_mma_native_kernel<NCH, KS, NT, MINB, 2><<<grid, NT, 0, h->stream>>>(                   \
             ngroups, nbrows, kptr, kcols, afrag, X, nsx, W, nsw, Y, nsy, ascale, afold, yscale, has_w, gpw, gpw <= 0,           \
-            h->mma_prefetch, h->mma_stream_policy, reverse);                                                           \
+            h->mma_prefetch, h->mma_stream_policy, reverse, glist);                                                    \
         else if (rotc) bsr_spmm_mma_native_kernel<NCH, KS, NT, MINB, 1><<<grid, NT, 0, h->stream>>>(                   \
             ngroups, nbrows, kptr, kcols, afrag, X, nsx, W, nsw, Y, nsy, ascale, afold, yscale, has_w, gpw, gpw <= 0,           \
-            h->mma_prefetch, h->mma_stream_policy, reverse);                                                           \
+            h->mma_prefetch, h->mma_stream_policy, reverse, glist);                                                    \
         else bsr_spmm_mma_native_kernel<NCH, KS, NT, MINB, 0><<<grid, NT, 0, h->stream>>>(                             \
             ngroups, nbrows, kptr, kcols, afrag, X, nsx, W, nsw, Y, nsy, ascale, afold, yscale, has_w, gpw, gpw <= 0,           \
-            h->mma_prefetch, h->mma_stream_policy, reverse);                                                           \
+            h->mma_prefetch, h->mma_stream_policy, reverse, glist);                                                    \
     } while (0)
     // (chunks of 16 columns, register-ring depth, threads per CTA, CTAs per SM); measured at C4 size, persistent schedule,
     // policy 7 (profiles/r01_spmm_mma_sweep.txt): 1: 0.828 ms | 0: 0.854 | 6: 0.851 | 5: 0.858 | 3: 0.864 | 2: 0.882

@@ -9,7 +9,6 @@ with all_reduce, after which every rank solves the identical small projected pro
 
 ``HaloPlan`` is pure index logic on torch tensors (CPU or CUDA) so it is covered by the world_size-2 gloo tests.
 """
-import weakref
 
 import numpy as np
 import torch
@@ -171,6 +170,7 @@ class PeerHalo:
         import ctypes
         from ._cabi import get_handle
         plan, d = op.plan, op.d
+        import os
         self.op, self.ncols = op, int(ncols)
         dev = op.indptr.device
         self.h = h = get_handle(dev.index)
@@ -178,57 +178,16 @@ class PeerHalo:
         world, rank, group = plan.world, plan.rank, plan.group
         row_bytes = d * self.ncols * 8
         ebytes = max(256, (plan.n_loc + plan.n_halo) * row_bytes)
-        sizes = [ebytes, ebytes, ebytes, 8 * max(world, 32)]          # three rotating block vectors + the flag array
-        self._own, self._opened = [], []
-        # the raw allocations outlive neither this object nor the process: close() is the orderly (collective) release,
-        # the finaliser the last resort when the object is dropped without it
-        self._finalizer = weakref.finalize(self, _release_ipc, lib, h._h, self._opened, self._own)
-
-        # Failure-atomic setup: every rank runs the SAME collectives whatever fails locally.
-        #   phase 1  local allocations only                     -> all_gather_object of (ok, handles)
-        #   phase 2  open the peers' handles (only if all ok)   -> all_reduce(MIN) of ok
-        # A failure on any rank makes every rank release what it holds and raise the same error.
-        err, handles = None, []
-        try:
-            for nbytes in sizes:
-                ptr = ctypes.c_void_p()
-                hd = (ctypes.c_uint8 * 64)()
-                rc = lib.rvgp_ipc_alloc(h._h, ctypes.c_int64(nbytes), ctypes.byref(ptr), hd)
-                if rc != 0:
-                    raise RuntimeError("rvgp_ipc_alloc: " + lib.rvgp_last_error(h._h).decode())
-                self._own.append(ptr.value)
-                handles.append(bytes(hd))
-        except Exception as e:
-            err = e
-        gathered = [None] * world
-        dist.all_gather_object(gathered, (err is None, handles), group=group)
-        if not all(g[0] for g in gathered):
-            self._finalizer()
-            raise RuntimeError("peer halo setup failed on rank(s) %s%s" %
-                               ([q for q, g in enumerate(gathered) if not g[0]], "" if err is None else ": %s" % (err,)))
-        table = [[None] * world for _ in sizes]                      # [buffer][rank] -> device address
-        try:
-            for b_i in range(len(sizes)):
-                for q in range(world):
-                    if q == rank:
-                        table[b_i][q] = self._own[b_i]
-                        continue
-                    pp = ctypes.c_void_p()
-                    hq = (ctypes.c_uint8 * 64).from_buffer_copy(gathered[q][1][b_i])
-                    rc = lib.rvgp_ipc_open(h._h, hq, ctypes.byref(pp))
-                    if rc != 0:
-                        raise RuntimeError("rvgp_ipc_open: " + lib.rvgp_last_error(h._h).decode())
-                    self._opened.append(pp.value)
-                    table[b_i][q] = pp.value
-        except Exception as e:
-            err = e
-        ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
-        if int(ok.item()) != 1:
-            self.close(collective=True)        # every rank is here: peers unmap before owners free
-            raise RuntimeError("peer halo setup failed (cudaIpcOpenMemHandle)%s" % ("" if err is None else ": %s" % (err,)))
-        self.E_ptrs = table[:3]                                       # [slot][rank] -> device address
-        self.flag_ptrs = table[3]
+        # The shared buffers come from a process-wide POOL (_IpcPool below): cudaMalloc + cudaIpcOpenMemHandle on every peer
+        # + the handle exchange cost tens of milliseconds per set, and a sharded create_data_object needs up to three sets.
+        # A set (three extended block vectors + the flag array) is reused by later operators whenever it is large enough;
+        # close() only returns it to the pool.  Sizes are agreed collectively (max over ranks) so that every rank takes the
+        # same pool decision.
+        self._set = _IpcPool.acquire(h, ebytes, world, rank, group, dev)
+        self._released = False
+        ebytes = self._set["cap"]
+        self.E_ptrs = self._set["E_ptrs"]                             # [slot][rank] -> device address
+        self.flag_ptrs = self._set["flag_ptrs"]
         nrows_ext = (plan.n_loc + plan.n_halo) * d
         self.E = [torch.as_tensor(_DevMem(self.E_ptrs[s][rank], ebytes), device=dev).view(torch.float64)[: nrows_ext * self.ncols]
                   .view(nrows_ext, self.ncols) for s in range(3)]
@@ -246,7 +205,7 @@ class PeerHalo:
         self.peer_slots = torch.tensor([self.flag_ptrs[q] + 8 * rank for q in peers] or [0], dtype=torch.int64, device=dev)
         self.wait_idx = torch.tensor(peers or [0], dtype=torch.int32, device=dev)
         self.err = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.epoch = 1
+        self.epoch = self._set["epoch"]           # epochs only grow, also across the users of a pooled set (the flags persist)
         L = op.local
         mp = L.mma if (d == 2 and getattr(L, "mma", None) is not None and self.ncols % 16 == 0) else None
         pat = L.mma_pattern if (d == 1 and getattr(L, "mma_pattern", None) is not None and self.ncols % 32 == 0) else None
@@ -259,7 +218,9 @@ class PeerHalo:
                         ("rotc", ctypes.c_int32), ("n_peers", ctypes.c_int32),
                         ("E", ctypes.c_void_p * 3), ("pull_src", ctypes.c_void_p * 3),
                         ("flags", ctypes.c_void_p), ("peer_slots", ctypes.c_void_p), ("wait_idx", ctypes.c_void_p),
-                        ("err", ctypes.c_void_p), ("timeout_ms", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                        ("err", ctypes.c_void_p), ("timeout_ms", ctypes.c_int32), ("n_interior", ctypes.c_int32),
+                        ("glist_interior", ctypes.c_void_p), ("glist_boundary", ctypes.c_void_p),
+                        ("n_boundary", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
         c = Ctx()
         c.n_loc, c.n_halo, c.d, c.ncols = plan.n_loc, plan.n_halo, d, self.ncols
@@ -273,6 +234,20 @@ class PeerHalo:
             c.rotc = int(rotc)
         elif pat is not None:            # scalar unit-weight Laplacian on the MMA kernel (spmm_mma.cu AMODE 2): no values streamed
             c.kptr, c.kcols, c.afrag, c.rotc = pat["kptr"].data_ptr(), pat["kcols"].data_ptr(), pat["deg"].data_ptr(), 2
+        if (mp is not None or pat is not None) and os.environ.get("RVGP_HALO_OVERLAP", "1") != "0":
+            # interior / boundary row-group lists (groups of 4 block rows, the unit of the MMA kernel): the interior launch of a
+            # step overlaps the neighbours' skew and the halo pull (csrc/halo.cu, halo_step)
+            ng = (plan.n_loc + 3) // 4
+            isb = torch.zeros(ng, dtype=torch.bool, device=dev)
+            if plan.boundary_rows.numel():
+                isb[(plan.boundary_rows.to(torch.int64) // 4)] = True
+            self._g_int = torch.nonzero(~isb).reshape(-1).to(torch.int32).contiguous()
+            self._g_bnd = torch.nonzero(isb).reshape(-1).to(torch.int32).contiguous()
+            if self._g_int.numel() == 0:
+                self._g_int = torch.zeros(1, dtype=torch.int32, device=dev)[:0]
+            c.glist_interior = self._g_int.data_ptr() if self._g_int.numel() else self._g_bnd.data_ptr()
+            c.glist_boundary = self._g_bnd.data_ptr() if self._g_bnd.numel() else self._g_int.data_ptr()
+            c.n_interior, c.n_boundary = int(self._g_int.numel()), int(self._g_bnd.numel())
         c.n_peers = len(peers)
         for s in range(3):
             c.E[s] = self.E_ptrs[s][rank]
@@ -303,20 +278,121 @@ class PeerHalo:
             raise RuntimeError("peer halo exchange timed out waiting for a neighbour rank (rvgp_halo_ctx.err)")
 
     def close(self, collective=True):
-        """Release the peer mappings and this rank's buffers.  ``collective=True`` (every rank calls it at the same point)
-        puts a barrier between the two so that no owner frees memory a peer still has mapped; ``collective=False`` is for
-        error paths where the other ranks may never arrive."""
-        if not self._finalizer.alive:
+        """Return the shared buffers to the pool (they stay mapped for the next operator; _IpcPool.release frees them).
+        Every rank must call it at the same point of the program, like every other step of the SPMD pipeline."""
+        if self._released:
             return
-        lib, hh = self.h.lib, self.h._h
+        self._released = True
+        torch.cuda.synchronize(self.err.device)
+        self._set["epoch"] = self.epoch + 2
+        self._set["in_use"] = False
+
+
+class _IpcPool:
+    """Process-wide pool of CUDA-IPC shared buffer sets for PeerHalo.  One set = three extended block vectors of `cap` bytes
+    + one flag array, allocated with rvgp_ipc_alloc on every rank and mapped into every peer (rvgp_ipc_open).  Sets are
+    created collectively and in the same order on every rank, and `acquire` picks by a size agreed with one all-reduce(MAX),
+    so all ranks always hold the same list and take the same decisions.  Memory is bounded by the largest operators seen;
+    `release()` (collective; also run at interpreter exit, non-collectively) unmaps and frees everything."""
+    sets = []
+
+    @staticmethod
+    def acquire(h, ebytes, world, rank, group, dev):
+        t = torch.tensor([int(ebytes)], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        need = int(t.item())
+        for st in _IpcPool.sets:
+            if not st["in_use"] and st["cap"] >= need and st["world"] == world and st["group"] is group:
+                st["in_use"] = True
+                return st
+        st = _IpcPool._create(h, need, world, rank, group, dev)
+        _IpcPool.sets.append(st)
+        return st
+
+    @staticmethod
+    def _create(h, cap, world, rank, group, dev):
         import ctypes
-        torch.cuda.synchronize(self.err.device if hasattr(self, "err") else None)
-        for p in self._opened:
-            lib.rvgp_ipc_close(hh, ctypes.c_void_p(p))
-        del self._opened[:]
-        if collective and dist.is_initialized():
-            dist.barrier(group=self.op.plan.group)
-        self._finalizer()                      # frees what is left (own buffers), exactly once
+        lib = h.lib
+        sizes = [cap, cap, cap, 8 * max(world, 32)]
+        own, opened = [], []
+        # Failure-atomic: every rank runs the SAME collectives whatever fails locally.
+        #   phase 1  local allocations only                     -> all_gather_object of (ok, handles)
+        #   phase 2  open the peers' handles (only if all ok)   -> all_reduce(MIN) of ok
+        # A failure on any rank makes every rank release what it holds and raise the same error.
+        err, handles = None, []
+        try:
+            for nbytes in sizes:
+                ptr = ctypes.c_void_p()
+                hd = (ctypes.c_uint8 * 64)()
+                rc = lib.rvgp_ipc_alloc(h._h, ctypes.c_int64(nbytes), ctypes.byref(ptr), hd)
+                if rc != 0:
+                    raise RuntimeError("rvgp_ipc_alloc: " + lib.rvgp_last_error(h._h).decode())
+                own.append(ptr.value)
+                handles.append(bytes(hd))
+        except Exception as e:
+            err = e
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (err is None, handles), group=group)
+        if not all(g[0] for g in gathered):
+            _release_ipc(lib, h._h, opened, own)
+            raise RuntimeError("peer halo setup failed on rank(s) %s%s" %
+                               ([q for q, g in enumerate(gathered) if not g[0]], "" if err is None else ": %s" % (err,)))
+        table = [[None] * world for _ in sizes]                      # [buffer][rank] -> device address
+        try:
+            for b_i in range(len(sizes)):
+                for q in range(world):
+                    if q == rank:
+                        table[b_i][q] = own[b_i]
+                        continue
+                    pp = ctypes.c_void_p()
+                    hq = (ctypes.c_uint8 * 64).from_buffer_copy(gathered[q][1][b_i])
+                    rc = lib.rvgp_ipc_open(h._h, hq, ctypes.byref(pp))
+                    if rc != 0:
+                        raise RuntimeError("rvgp_ipc_open: " + lib.rvgp_last_error(h._h).decode())
+                    opened.append(pp.value)
+                    table[b_i][q] = pp.value
+        except Exception as e:
+            err = e
+        ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) != 1:
+            for p in opened:
+                lib.rvgp_ipc_close(h._h, ctypes.c_void_p(p))
+            del opened[:]
+            dist.barrier(group=group)                                 # peers unmap before owners free
+            _release_ipc(lib, h._h, opened, own)
+            raise RuntimeError("peer halo setup failed (cudaIpcOpenMemHandle)%s" % ("" if err is None else ": %s" % (err,)))
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=group)                                     # every rank has opened every handle before the first pull
+        return dict(cap=cap, world=world, group=group, E_ptrs=table[:3], flag_ptrs=table[3], epoch=1, in_use=True,
+                    lib=lib, hh=h._h, opened=opened, own=own)
+
+    @staticmethod
+    def release(collective=True):
+        """Unmap and free every pooled set.  collective=True: all ranks call it together (peers unmap, barrier, owners free)."""
+        import ctypes
+        sets, _IpcPool.sets = _IpcPool.sets, []
+        if not sets:
+            return
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        for st in sets:
+            for p in st["opened"]:
+                st["lib"].rvgp_ipc_close(st["hh"], ctypes.c_void_p(p))
+            del st["opened"][:]
+        if collective and dist.is_available() and dist.is_initialized():
+            dist.barrier()
+        for st in sets:
+            _release_ipc(st["lib"], st["hh"], st["opened"], st["own"])
+
+
+def release_ipc_pool(collective=True):
+    """Free the pooled CUDA-IPC halo buffers of this process (call on every rank, e.g. before destroy_process_group)."""
+    _IpcPool.release(collective=collective)
+
+
+import atexit as _atexit
+_atexit.register(lambda: _IpcPool.release(collective=False))
 
 
 def _release_ipc(lib, hh, opened, own):

@@ -26,6 +26,12 @@ struct Handle {
     int mma_variant_n2;           // tuning: the same for panels of 32 native columns (2 chunks)
     int mma_prefetch;             // tuning: L2 prefetch distance (warp iterations) of the native-layout MMA SpMM
     int mma_stream_policy;        // tuning: bit0 = no-L1-allocate W loads, bit1 = no-L1-allocate Y stores (MMA SpMM)
+    // CUDA graph of the rank-k GP evaluation (rvgp_gp_lowrank_eval_f64): ~110 tiny launches replayed with one cudaGraphLaunch
+    cudaGraphExec_t gp_graph;     // nullptr until captured
+    const void* gp_graph_key[6];  // k (as pointer-sized int) and the five buffers the captured launches were recorded with
+    unsigned long long gp_graph_launches;
+    cudaStream_t gp_stream;       // blocking side stream used when the handle follows the legacy default stream (not capturable)
+    int gp_graph_off;             // 1: capture failed once, run eagerly from now on (or rvgp_set_option("gp_graph", 0))
 };
 
 inline Handle* H(rvgp_handle_t h) { return reinterpret_cast<Handle*>(h); }

@@ -27,6 +27,11 @@ extern "C" int rvgp_create(int device, rvgp_handle_t* out) {
     h->mma_variant = 1;
     h->mma_variant_n2 = 1;   // (2 chunks, ring 2, 256 threads x 3 CTAs/SM): 0.423 vs 0.448 ms for the 64-column L panels (profiles/r02_k9_sweep.txt)
     h->mma_prefetch = 1;
+    h->gp_graph = nullptr;
+    h->gp_graph_launches = 0;
+    h->gp_stream = nullptr;
+    h->gp_graph_off = 0;
+    for (int i = 0; i < 6; ++i) h->gp_graph_key[i] = nullptr;
     h->last_error[0] = 0;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete h; return RVGP_ERR_CUDA; }
@@ -36,6 +41,10 @@ extern "C" int rvgp_create(int device, rvgp_handle_t* out) {
 }
 
 extern "C" int rvgp_destroy(rvgp_handle_t hh) {
+    if (hh) {
+        if (H(hh)->gp_graph) cudaGraphExecDestroy(H(hh)->gp_graph);
+        if (H(hh)->gp_stream) cudaStreamDestroy(H(hh)->gp_stream);
+    }
     delete H(hh);
     return RVGP_OK;
 }
@@ -62,5 +71,6 @@ extern "C" int rvgp_set_option(rvgp_handle_t hh, const char* key, int value) {
     if (strcmp(key, "mma_prefetch") == 0) { H(hh)->mma_prefetch = value; return RVGP_OK; }
     if (strcmp(key, "mma_gpw") == 0) { H(hh)->mma_gpw = value; return RVGP_OK; }
     if (strcmp(key, "mma_stream_policy") == 0) { H(hh)->mma_stream_policy = value; return RVGP_OK; }
+    if (strcmp(key, "gp_graph") == 0) { H(hh)->gp_graph_off = value ? 0 : 1; return RVGP_OK; }
     return set_error(H(hh), RVGP_ERR_BAD_ARG, "unknown option %s%s", key);
 }

@@ -259,12 +259,9 @@ extern "C" int64_t rvgp_gp_lowrank_eval_workspace_bytes(int k) {
     return dbl * (int64_t)sizeof(double) + rvgp_potrf_workspace_bytes(k) + rvgp_coldot_workspace_bytes(k, k) + 256;
 }
 
-extern "C" int rvgp_gp_lowrank_eval_f64(rvgp_handle_t hh, int k, const double* G, const double* b, const double* par,
-                                        double* out, void* workspace, int64_t workspace_bytes) {
+static int gp_lowrank_eval_enqueue(rvgp_handle_t hh, int k, const double* G, const double* b, const double* par, double* out,
+                                   void* workspace) {
     Handle* h = H(hh);
-    RVGP_REQUIRE(h, k >= 1, "gp_lowrank_eval: k >= 1");
-    if (rvgp_gp_lowrank_eval_workspace_bytes(k) > workspace_bytes)
-        return set_error(h, RVGP_ERR_CAPACITY, "gp_lowrank_eval: workspace too small%s%s");
     double* B = (double*)workspace;
     double* Q = B + (int64_t)k * k;
     double* rhs = Q + (int64_t)k * k;
@@ -288,5 +285,59 @@ extern "C" int rvgp_gp_lowrank_eval_f64(rvgp_handle_t hh, int k, const double* G
     if ((rc = rvgp_logdiag_sum_f64(hh, B, k, k, logdet))) return rc;
     gp_lowrank_pack_kernel<<<cdiv(k, 256), 256, 0, h->stream>>>(k, flag, logdet, rhs, qs, out);
     RVGP_LAUNCH_OK(h, "gp_lowrank_pack_kernel");
+    return RVGP_OK;
+}
+
+// The evaluation is ~110 tiny launches (64-wide Cholesky panels and triangular solves of a k x k matrix): it is captured into
+// a CUDA graph on first use and replayed with ONE cudaGraphLaunch while (k, G, b, par, out, workspace) stay the same -- which
+// they do for the ~100 evaluations of a fit.  The legacy default stream cannot be captured, so a handle that follows it uses
+// a BLOCKING side stream (implicitly ordered with the legacy stream on both sides).  Any capture failure falls back to eager
+// launches for the rest of the handle's life.
+extern "C" int rvgp_gp_lowrank_eval_f64(rvgp_handle_t hh, int k, const double* G, const double* b, const double* par,
+                                        double* out, void* workspace, int64_t workspace_bytes) {
+    Handle* h = H(hh);
+    RVGP_REQUIRE(h, k >= 1, "gp_lowrank_eval: k >= 1");
+    if (rvgp_gp_lowrank_eval_workspace_bytes(k) > workspace_bytes)
+        return set_error(h, RVGP_ERR_CAPACITY, "gp_lowrank_eval: workspace too small%s%s");
+    if (h->gp_graph_off) return gp_lowrank_eval_enqueue(hh, k, G, b, par, out, workspace);
+    const void* key[6] = {(const void*)(intptr_t)k, G, b, par, out, workspace};
+    cudaStream_t user = h->stream;
+    cudaStream_t run = user;
+    if (user == nullptr || user == cudaStreamLegacy) {
+        if (h->gp_stream == nullptr && cudaStreamCreate(&h->gp_stream) != cudaSuccess) { h->gp_graph_off = 1; cudaGetLastError(); }
+        if (h->gp_graph_off) return gp_lowrank_eval_enqueue(hh, k, G, b, par, out, workspace);
+        run = h->gp_stream;
+    }
+    if (h->gp_graph != nullptr && memcmp(key, h->gp_graph_key, sizeof(key)) != 0) {
+        cudaGraphExecDestroy(h->gp_graph);
+        h->gp_graph = nullptr;
+    }
+    if (h->gp_graph == nullptr) {
+        const unsigned long long l0 = h->launches;
+        cudaGraph_t graph = nullptr;
+        // warm the lazily loaded kernels / attributes OUTSIDE the capture (first evaluation of a fit runs eagerly)
+        h->stream = run;
+        int rc = gp_lowrank_eval_enqueue(hh, k, G, b, par, out, workspace);
+        if (rc) { h->stream = user; return rc; }
+        bool ok = cudaStreamBeginCapture(run, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (ok) {
+            rc = gp_lowrank_eval_enqueue(hh, k, G, b, par, out, workspace);
+            ok = (cudaStreamEndCapture(run, &graph) == cudaSuccess) && rc == RVGP_OK && graph != nullptr;
+        }
+        h->stream = user;
+        if (ok) ok = cudaGraphInstantiate(&h->gp_graph, graph, 0) == cudaSuccess;
+        if (graph) cudaGraphDestroy(graph);
+        if (!ok) {
+            cudaGetLastError();
+            h->gp_graph = nullptr;
+            h->gp_graph_off = 1;                   // the eager evaluation above already produced this call's result
+            return RVGP_OK;
+        }
+        memcpy(h->gp_graph_key, key, sizeof(key));
+        h->gp_graph_launches = (h->launches - l0) / 2;
+        return RVGP_OK;                            // result of this call: the eager run above
+    }
+    RVGP_CUDA_OK(h, cudaGraphLaunch(h->gp_graph, run));
+    h->launches += h->gp_graph_launches;
     return RVGP_OK;
 }

@@ -44,14 +44,34 @@ def compute_vectorfield_features_time(timepoints, positions, vectors, k=5, refer
 
 
 def interpolate_timepoint(d, train_idx, test_idx, project=True, t=0, plot=False, dim_emb=3, dim_man=2, n_eigenpairs=50):
-    """eeg_utils.py:83-116 (the t > 0 sub-graph diffusion branch of the reference needs ``d.Lc.A`` on a node subset and is
-    not provided; t = 0 is what interpolate_time_range uses)."""
+    """eeg_utils.py:83-116.  ``project``: the signal at the training nodes is expressed in the local frames, optionally diffused
+    for time ``t`` on the SUB-GRAPH of the training nodes (principal sub-matrices of Lc and L, :99-104), and mapped back.  The
+    sub-matrices are sliced sparsely (the reference goes through the dense ``d.Lc.A``) and the diffusion is the Chebyshev
+    exp(-tA) action of smoothing.vector_diffusion(method="matrix_exp") on the device."""
     import RVGP
     if project:
-        d.vectors = project_to_local_frame(d.vectors, d.gauges[train_idx, :, :])
+        # The reference replaces d.vectors by the (n_train, D) result, which its own train_gp then indexes with node ids
+        # (main.py:25) -> IndexError unless the training nodes are 0..n_train-1.  Here the processed rows are written back
+        # into a full (n, D) field (identical whenever the reference works; defined in all other cases).
+        train_idx = np.asarray(train_idx)
+        full = np.array(d.vectors, dtype=np.float64, copy=True)
+        if full.shape[0] == len(train_idx) and full.shape[0] != d.n:        # caller passed the training rows only
+            tmp = np.zeros((d.n, full.shape[1]))
+            tmp[train_idx] = full
+            full = tmp
+        v = project_to_local_frame(full[train_idx], d.gauges[train_idx, :, :])
         if t > 0:
-            raise NotImplementedError("sub-graph diffusion before the fit (eeg_utils.py:99-104) is not provided")
-        d.vectors = project_to_local_frame(d.vectors, d.gauges[train_idx, :, :], reverse=True)
+            from scipy import sparse
+            from .geometry import compute_laplacian
+            from .smoothing import vector_diffusion
+            dm = d.gauges.shape[2]
+            Lc_idx = np.sort(np.hstack([train_idx * dm + q for q in range(dm)]))     # the reference hard-codes dm = 2 (:100)
+            Lc_ = sparse.bsr_matrix(d.Lc.tocsr()[Lc_idx, :][:, Lc_idx], blocksize=(dm, dm))
+            L = compute_laplacian(d._graph if hasattr(d, "_graph") else d.G)
+            L = L[train_idx, :][:, train_idx]
+            v = vector_diffusion(v, t, L=L, Lc=Lc_, method="matrix_exp")
+        full[train_idx] = project_to_local_frame(v, d.gauges[train_idx, :, :], reverse=True)
+        d.vectors = full
     gp = RVGP.fit(d, train_ind=train_idx, epochs=100, noise_variance=0.001)
     f_pred, _ = gp.transform(d, test_idx)
     return f_pred

@@ -210,3 +210,65 @@ def test_transform_with_float_positional_encodings():
     assert m_f.shape == (120, 1)
     np.testing.assert_allclose(m_f.reshape(40, 3), m_int, rtol=1e-12, atol=1e-14)
     np.testing.assert_allclose(v_f.reshape(40, 3), v_int, rtol=1e-12, atol=1e-14)
+
+
+def test_interpolate_timepoint_subgraph_diffusion_matches_dense_expm():
+    """eeg_utils.interpolate_timepoint(project=True, t>0) (examples/eeg_example/eeg_utils.py:96-106): the training-node signal is
+    diffused on the SUB-GRAPH (principal sub-matrices of Lc and L) before the fit.  The device path (sparse slices + Chebyshev
+    exp(-tA) action) is checked against the reference's dense scipy.linalg.expm recipe via the oracle."""
+    import contextlib
+    import io
+    import scipy.sparse as sp
+    import RVGP
+    from rvgp_b200 import eeg_utils
+    from rvgp_b200 import params as P
+    from oracle import rvgp_oracle as O
+    from tests.workloads import make_cloud
+    X = make_cloud("sphere", 600, 3)
+    d = RVGP.create_data_object(X, n_eigenpairs=20, verbose=False)
+    d.random_vector_field(seed=2)
+    field = d.vectors.copy()
+    rng = np.random.RandomState(1)
+    train_idx = np.sort(rng.choice(600, 200, replace=False))
+    test_idx = np.setdiff1d(np.arange(600), train_idx)
+    t = 3.0
+    # reference recipe on the host (dense expm, restated in the oracle)
+    g = d.gauges[train_idx]
+    v = O.express_in_local_frame(field[train_idx], g)
+    Lc_idx = np.sort(np.hstack([train_idx * 2, train_idx * 2 + 1]))
+    Lc_ = sp.bsr_matrix(d.Lc.tocsr()[Lc_idx][:, Lc_idx], blocksize=(2, 2))
+    L_ = d.L[train_idx][:, train_idx]
+    v = O.vector_diffusion(v, t, L_, Lc_, dense=True)
+    want = field.copy()
+    want[train_idx] = O.express_in_local_frame(np.asarray(v), g, reverse=True)
+    P.set_default_positive_minimum(0.0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        pred = eeg_utils.interpolate_timepoint(d, train_idx, test_idx, project=True, t=t)
+    np.testing.assert_allclose(d.vectors, want, atol=1e-9)          # the smoothed field that was fitted
+    assert pred.shape == (len(test_idx), 3) and np.all(np.isfinite(pred))
+
+
+def test_affinity_graph_matches_reference_recipe():
+    """manifold_graph(typ='affinity') (geometry.py:114-118): dense Gaussian-kernel weights on the device == the reference's
+    sklearn / numpy recipe, and its Laplacian == networkx's."""
+    import networkx as nx
+    import scipy.sparse as sp
+    from sklearn.metrics import pairwise_distances
+    from rvgp_b200 import geometry as geo
+    from tests.workloads import make_cloud
+    X = make_cloud("sphere", 300, 5)
+    G = geo.manifold_graph(X, typ="affinity")
+    A_ref = np.exp(-pairwise_distances(X) ** 2 / (2 * 0.1 ** 2))
+    A = G.weights.reshape(300, 300).cpu().numpy()
+    assert np.abs(A - A_ref).max() < 1e-12 and np.all(np.diag(A) == 1.0)
+    Gn = G.to_networkx()
+    Gr = nx.from_numpy_array(A_ref)
+    assert Gn.number_of_edges() == Gr.number_of_edges() and np.allclose(Gn.nodes[7]["pos"], X[7])
+    L = geo.compute_laplacian(G)
+    Lr = sp.csr_matrix(nx.laplacian_matrix(Gr), dtype=np.float64)
+    assert abs(L - Lr).max() < 1e-11
+    with pytest.raises(NotImplementedError):
+        import ptu_dijkstra
+        ptu_dijkstra.tangent_frames(X, Gn, 2, 15)                     # weighted graph: refused, not silently unit-weighted
+    with pytest.raises(ValueError):
+        geo.manifold_graph(X, typ="nope")

@@ -71,13 +71,13 @@ def spectral_action(evals, U, x, t, h=None):
     return out, proj_coef
 
 
-def diffuse(A, x, t, evals=None, U=None, hi=None, tol=1e-12, stats=None):
+def diffuse(A, x, t, evals=None, U=None, hi=None, tol=1e-12, stats=None, lo=0.0):
     """exp(-t A) x.  With an eigenbasis (evals ascending, U unit-norm): spectral part + Chebyshev action on the
     deflated remainder when exp(-t*evals[-1]) > tol.  Without: Chebyshev on [0, hi]."""
     h = get_handle(x.device.index)
     x = x.contiguous()
     if evals is None:
-        return cheb_expm_action(A, x, t, 0.0, hi, stats=stats)
+        return cheb_expm_action(A, x, t, float(lo), hi, stats=stats)
     out, pc = spectral_action(evals, U, x, t, h)
     lam_k = float(evals[-1].item())
     trunc = math.exp(-t * max(lam_k, 0.0))
@@ -94,17 +94,17 @@ def diffuse(A, x, t, evals=None, U=None, hi=None, tol=1e-12, stats=None):
     return out
 
 
-def vector_diffusion_device(x_local, t, Lc, L, eig_Lc=None, eig_L=None, hi=None, normalise=True, stats=None):
+def vector_diffusion_device(x_local, t, Lc, L, eig_Lc=None, eig_L=None, hi=None, normalise=True, stats=None, lo=(0.0, 0.0)):
     """smoothing.py:37-64 on device tensors.  x_local (n, d) local coordinates; Lc, L BsrMatrix;
     eig_* = (evals, unit-norm evecs) or None."""
     h = get_handle(x_local.device.index)
     n, d = x_local.shape
-    out = diffuse(Lc, x_local.reshape(n * d, 1), t, *(eig_Lc or (None, None)), hi=hi, stats=stats).reshape(n, d)
+    out = diffuse(Lc, x_local.reshape(n * d, 1), t, *(eig_Lc or (None, None)), hi=hi, stats=stats, lo=lo[0]).reshape(n, d)
     if normalise:
         x_abs = torch.empty((n, 1), dtype=torch.float64, device=x_local.device)
         h.call("rvgp_row_norms_f64", I64(n), int(d), x_local.contiguous(), x_abs)
         both = torch.cat([x_abs, torch.ones_like(x_abs)], dim=1).contiguous()      # [|x|, 1]
-        res = diffuse(L, both, t, *(eig_L or (None, None)), hi=hi)
+        res = diffuse(L, both, t, *(eig_L or (None, None)), hi=hi, lo=lo[1])
         out_abs = res[:, 0].contiguous()
         ind = res[:, 1].contiguous()
         out = out.contiguous()
@@ -125,8 +125,16 @@ def _bsr_from_scipy(M, dev):
     vals = torch.from_numpy(np.ascontiguousarray(B.data, dtype=np.float64).reshape(-1, d, d)).to(dev)
     A = BsrMatrix(M.shape[0] // d, d, torch.from_numpy(B.indptr.astype(np.int32)).to(dev),
                   torch.from_numpy(B.indices.astype(np.int32)).to(dev), vals)
-    hi = float(abs(sparse.csr_matrix(M)).sum(1).max())
-    return A, hi
+    C = sparse.csr_matrix(M)
+    absrow = np.asarray(abs(C).sum(1)).reshape(-1)
+    hi = float(absrow.max())
+    # Gershgorin LOWER bound (symmetric matrices): min_i (a_ii - sum_{j != i} |a_ij|), clamped at 0.  It is 0 for a full graph
+    # Laplacian, but positive for principal sub-matrices (eeg_utils.interpolate_timepoint diffuses on the sub-graph of the
+    # training nodes): starting the Chebyshev expansion of exp(-t A) at lo keeps its accuracy RELATIVE to exp(-t lo) ||x||
+    # instead of ||x||, which matters when the result is renormalised afterwards (smoothing.py:56-61)
+    diag = C.diagonal()
+    lo = float(max(0.0, (2.0 * diag - absrow).min())) if C.shape[0] else 0.0
+    return A, hi, lo
 
 
 def scalar_diffusion(x, t, method="matrix_exp", par=None):
@@ -137,8 +145,8 @@ def scalar_diffusion(x, t, method="matrix_exp", par=None):
     if xd.dim() == 1:
         xd = xd.unsqueeze(1)
     if method == "matrix_exp":
-        A, hi = _bsr_from_scipy(par, xd.device)
-        return cheb_expm_action(A, xd, float(t), 0.0, hi).cpu().numpy()
+        A, hi, lo = _bsr_from_scipy(par, xd.device)
+        return cheb_expm_action(A, xd, float(t), lo, hi).cpu().numpy()
     if method == "spectral":
         assert isinstance(par, (list, tuple)) and len(par) == 2, \
             "For spectral method, par must be a tuple of eigenvalues, eigenvectors!"
@@ -159,9 +167,9 @@ def vector_diffusion(x, t, Lc, L=None, method="spectral", normalise=True):
         assert L is not None, "Need Laplacian for normalised diffusion!"
     xd = to_device_f64(x)
     if method == "matrix_exp":
-        A_c, hi_c = _bsr_from_scipy(Lc, xd.device)
-        A_s, hi_s = _bsr_from_scipy(L, xd.device) if normalise else (None, 0.0)
-        out = vector_diffusion_device(xd, float(t), A_c, A_s, hi=max(hi_c, hi_s), normalise=normalise)
+        A_c, hi_c, lo_c = _bsr_from_scipy(Lc, xd.device)
+        A_s, hi_s, lo_s = _bsr_from_scipy(L, xd.device) if normalise else (None, 0.0, 0.0)
+        out = vector_diffusion_device(xd, float(t), A_c, A_s, hi=max(hi_c, hi_s), normalise=normalise, lo=(lo_c, lo_s))
     elif method == "spectral":
         assert len(Lc) == 2, "Lc must be a tuple of eigenvalues, eigenvectors!"
         eig_c = (to_device_f64(Lc[0]), to_device_f64(Lc[1]))

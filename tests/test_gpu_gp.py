@@ -231,7 +231,7 @@ def test_interpolate_timepoint_subgraph_diffusion_matches_dense_expm():
     rng = np.random.RandomState(1)
     train_idx = np.sort(rng.choice(600, 200, replace=False))
     test_idx = np.setdiff1d(np.arange(600), train_idx)
-    t = 3.0
+    t = 0.3          # the sub-graph of a third of the nodes is strongly diagonally dominant: exp(-t A) decays like exp(-7 t)
     # reference recipe on the host (dense expm, restated in the oracle)
     g = d.gauges[train_idx]
     v = O.express_in_local_frame(field[train_idx], g)
@@ -244,7 +244,7 @@ def test_interpolate_timepoint_subgraph_diffusion_matches_dense_expm():
     P.set_default_positive_minimum(0.0)
     with contextlib.redirect_stdout(io.StringIO()):
         pred = eeg_utils.interpolate_timepoint(d, train_idx, test_idx, project=True, t=t)
-    np.testing.assert_allclose(d.vectors, want, atol=1e-9)          # the smoothed field that was fitted
+    np.testing.assert_allclose(d.vectors, want, atol=1e-8)          # the smoothed field that was fitted
     assert pred.shape == (len(test_idx), 3) and np.all(np.isfinite(pred))
 
 

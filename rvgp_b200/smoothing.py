@@ -37,7 +37,10 @@ def cheb_expm_action(A, x, t, lo, hi, tol=1e-14, stats=None):
     keep = np.nonzero(np.abs(coef) > tol * np.abs(coef).max())[0]
     deg = int(keep.max()) if keep.size else 0
     out = torch.zeros_like(x)
-    Tprev = x.contiguous()
+    # the three-term recurrence ROTATES its buffers, so from the third term on it writes into the one that held T_0: that must
+    # never be the caller's x (round-2 finding: vector_diffusion(method="matrix_exp", normalise=True) computed |x| from an x the
+    # connection-Laplacian diffusion had already overwritten)
+    Tprev = x.clone() if deg >= 2 else x.contiguous()
     _axpy(h, coef[0], Tprev, out)
     if deg >= 1:
         s = 2.0 / (hi - lo)

@@ -467,8 +467,7 @@ def smallest_eigenpairs(A, k, upper_bound, lower_bound=0.0, tol=1e-12, nex=None,
             G = dense.sym_to_host(Gd)
             t0 = time.perf_counter()
             with _lapack_ctx():
-                R, shifted = _chol_upper_shifted(G)
-                Rinv = _tri_inv_upper(R)
+                Rinv, shifted = _cholqr_factor(G, dev)
             st["t_host"] += time.perf_counter() - t0
             Cd.copy_(torch.from_numpy(np.ascontiguousarray(Rinv)))
             dense.apply(V, Cd, W)                          # W = V R^-1   (nearly orthonormal)
@@ -485,12 +484,7 @@ def smallest_eigenpairs(A, k, upper_bound, lower_bound=0.0, tol=1e-12, nex=None,
         Hm = dense.sym_to_host(Hd)
         t0 = time.perf_counter()
         with _lapack_ctx():
-            R2 = np.linalg.cholesky(G).T
-            R2inv = _tri_inv_upper(R2)
-            Hm = R2inv.T @ Hm @ R2inv
-            Hm = 0.5 * (Hm + Hm.T)
-            theta, Y = np.linalg.eigh(Hm)
-            Cm = R2inv @ Y
+            theta, Cm = _rayleigh_ritz_small(G, Hm, dev)
         st["t_host"] += time.perf_counter() - t0
         Cd.copy_(torch.from_numpy(np.ascontiguousarray(Cm)))
         theta_d.copy_(torch.from_numpy(theta))
@@ -571,6 +565,69 @@ def lanczos_upper_bound(A, steps=24, seed=12345, comm=None, h=None):
     T = np.diag(alphas) + np.diag(betas[:-1], 1) + np.diag(betas[:-1], -1)
     theta = np.linalg.eigvalsh(T)
     return float(theta[-1] + abs(betas[-1]))
+
+
+
+# ---- the m x m projected problems -------------------------------------------------------------------------------------------
+# Small blocks (m < 192) are factorised with host LAPACK (a few BLAS threads, _lapack_ctx); larger ones on the GPU through
+# torch.linalg (cuSOLVER): measured on the B200 box (tools/eigh_probe.py, profiles/r02f_eigh_probe.txt) a 1280 x 1280 real eigh
+# takes 20 ms there against 86 ms on 16 host cores and 266 ms on one -- and under torchrun every rank has only a few cores, so at
+# 8 GPUs the host factorisations were the serial floor of the eigensolver.  RVGP_HOST_EIGH=1 forces the host path.
+import os as _os_mod
+_HOST_EIGH = _os_mod.environ.get("RVGP_HOST_EIGH", "0") == "1"
+_DEVICE_MIN = 192
+
+
+def _on_device(m, dev):
+    return (not _HOST_EIGH) and m >= _DEVICE_MIN and dev is not None and dev.type == "cuda"
+
+
+def _cholqr_factor(G, dev=None):
+    """Upper Cholesky factor R of the Hermitian Gram matrix G (G = R^H R; shifted on breakdown) and R^-1.
+    Returns (Rinv (host), shifted)."""
+    m = G.shape[0]
+    if _on_device(m, dev):
+        Gt = torch.from_numpy(np.ascontiguousarray(G)).to(dev)
+        L, info = torch.linalg.cholesky_ex(Gt)
+        shifted = False
+        if int(info.item()) != 0:
+            shifted = True
+            shift = 1e-13 * m
+            eye = torch.eye(m, dtype=Gt.dtype, device=dev)
+            while True:
+                L, info = torch.linalg.cholesky_ex(Gt + shift * eye)
+                if int(info.item()) == 0:
+                    break
+                shift *= 100.0
+                if shift > 1.0:
+                    raise np.linalg.LinAlgError("Gram matrix is not positive definite even with a unit shift")
+        eye = torch.eye(m, dtype=Gt.dtype, device=dev)
+        Rinv = torch.linalg.solve_triangular(L.mH, eye, upper=True)          # R = L^H
+        return Rinv.cpu().numpy(), shifted
+    R, shifted = (_chol_upper_shifted_c(G) if np.iscomplexobj(G) else _chol_upper_shifted(G))
+    return _tri_inv_upper(R), shifted
+
+
+def _rayleigh_ritz_small(G, Hm, dev=None):
+    """Generalised Hermitian eigenproblem H y = theta G y of the (nearly orthonormal) block: R = chol(G) upper,
+    eigh(R^-H H R^-1), coefficients R^-1 Y.  Returns (theta ascending (host), Cm (host))."""
+    m = G.shape[0]
+    if _on_device(m, dev):
+        Gt = torch.from_numpy(np.ascontiguousarray(G)).to(dev)
+        Ht = torch.from_numpy(np.ascontiguousarray(Hm)).to(dev)
+        L = torch.linalg.cholesky(Gt)                                          # G = L L^H, R = L^H
+        X = torch.linalg.solve_triangular(L, Ht, upper=False)                   # L^-1 H
+        Hp = torch.linalg.solve_triangular(L, X.mH, upper=False).mH             # L^-1 H L^-H = R^-H H R^-1
+        Hp = 0.5 * (Hp + Hp.mH)
+        theta, Y = torch.linalg.eigh(Hp)
+        Cm = torch.linalg.solve_triangular(L.mH, Y, upper=True)                 # R^-1 Y
+        return theta.cpu().numpy(), Cm.cpu().numpy()
+    R2 = np.linalg.cholesky(G).conj().T
+    R2inv = _tri_inv_upper(R2)
+    Hp = R2inv.conj().T @ Hm @ R2inv
+    Hp = 0.5 * (Hp + Hp.conj().T)
+    theta, Y = np.linalg.eigh(Hp)
+    return theta, R2inv @ Y
 
 
 def _chol_upper_shifted(G):
@@ -776,8 +833,7 @@ def smallest_eigenpairs_paired(A, k, upper_bound, lower_bound=0.0, tol=1e-12, ne
             G = gram_c(V, JV, V, Gr, Gi)
             t0 = time.perf_counter()
             with _lapack_ctx():
-                R, shifted = _chol_upper_shifted_c(G)
-                Rinv = _tri_inv_upper(R)
+                Rinv, shifted = _cholqr_factor(G, dev)
             st["t_host"] += time.perf_counter() - t0
             apply_c(V, JV, Rinv, W)
             V, W = W, V
@@ -791,12 +847,7 @@ def smallest_eigenpairs_paired(A, k, upper_bound, lower_bound=0.0, tol=1e-12, ne
         Hm = gram_c(V, JV, W, Hr, Hi)                      # V^H A V
         t0 = time.perf_counter()
         with _lapack_ctx():
-            R2 = np.linalg.cholesky(G).conj().T
-            R2inv = _tri_inv_upper(R2)
-            Hm = R2inv.conj().T @ Hm @ R2inv
-            Hm = 0.5 * (Hm + Hm.conj().T)
-            theta, Y = np.linalg.eigh(Hm)
-            Cm = R2inv @ Y
+            theta, Cm = _rayleigh_ritz_small(G, Hm, dev)
         st["t_host"] += time.perf_counter() - t0
         theta_d.copy_(torch.from_numpy(np.ascontiguousarray(theta)))
         apply_c(V, JV, Cm, W)                              # Ritz vectors

@@ -346,3 +346,33 @@ def test_cheb_filter_mma_pattern_matches_gather(degree):
     assert np.abs(outs[1][:, :64] - V0[:, :64].cpu().numpy()).max() == 0.0
     assert np.abs(outs[1][:, 128:] - V0[:, 128:].cpu().numpy()).max() == 0.0
     assert np.abs(outs[0] - outs[1]).max() <= 1e-11 * np.abs(outs[0]).max()
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_projected_problem_device_path_matches_host_lapack(cplx):
+    """The m x m projected problems of the eigensolvers (CholeskyQR factor, Rayleigh-Ritz) run on the GPU for m >= 192
+    (eigensolver._cholqr_factor / _rayleigh_ritz_small): same results as the host LAPACK path, incl. the shifted Cholesky."""
+    from rvgp_b200 import eigensolver as E
+    rng = np.random.default_rng(0)
+    m = 256
+    B = rng.normal(size=(m, 3 * m)) + (1j * rng.normal(size=(m, 3 * m)) if cplx else 0)
+    G = B @ B.conj().T / (3 * m)
+    A = rng.normal(size=(m, m)) + (1j * rng.normal(size=(m, m)) if cplx else 0)
+    H = A + A.conj().T
+    dev = _dev()
+    assert E._on_device(m, dev) and not E._on_device(64, dev)
+    Rinv_d, sh_d = E._cholqr_factor(G, dev)
+    Rinv_h, sh_h = E._cholqr_factor(G, None)
+    assert not sh_d and not sh_h and np.abs(Rinv_d - Rinv_h).max() <= 1e-11 * np.abs(Rinv_h).max()
+    assert np.abs(np.triu(Rinv_d) - Rinv_d).max() == 0.0 or np.abs(np.tril(Rinv_d, -1)).max() < 1e-14
+    th_d, C_d = E._rayleigh_ritz_small(G, H, dev)
+    th_h, C_h = E._rayleigh_ritz_small(G, H, None)
+    np.testing.assert_allclose(th_d, th_h, rtol=1e-11, atol=1e-11)
+    # eigenvectors up to phase: C^H G C = I and H C = G C theta
+    for C, th in ((C_d, th_d), (C_h, th_h)):
+        assert np.abs(C.conj().T @ G @ C - np.eye(m)).max() < 1e-10
+        assert np.abs(H @ C - (G @ C) * th).max() < 1e-9 * np.abs(H).max()
+    Gs = G.copy()
+    Gs[1] = Gs[0]; Gs[:, 1] = Gs[:, 0]                               # exactly singular -> shifted factor, flagged
+    _, sh = E._cholqr_factor(Gs - 1e-9 * np.eye(m), dev)
+    assert sh

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the RVGP hot path on B200 (contract: see the task brief / DESIGN.md section 10).
+"""bench.py -- headline benchmark of the RVGP hot path on B200 (contract: see the task brief / DESIGN.md section 9).
 
 One "step" = create_data_object + fit + transform on a synthetic point cloud (BASELINE.json metric:
 "create_data_object+fit+transform wall-s at 1M pts/k=500; Lanczos SpMM GB/s").

@@ -2,7 +2,7 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from tools.profile_spmm import build
+from tools._build import build
 from rvgp_b200._cabi import get_handle
 kind, n, which, b, lpr = sys.argv[1], int(sys.argv[2]), sys.argv[3], int(sys.argv[4]), int(sys.argv[5])
 A, L, _ = build(kind, n)

@@ -4,7 +4,7 @@ usage: python tools/profile_mma.py [torus 1000000] [quick]"""
 import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from tools.profile_spmm import build
+from tools._build import build
 from rvgp_b200._cabi import get_handle
 
 kind = sys.argv[1] if len(sys.argv) > 1 else "torus"

@@ -1,7 +1,7 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from tools.profile_spmm import build
+from tools._build import build
 from rvgp_b200._cabi import get_handle
 A, L, _ = build("torus", 1000000)
 h = get_handle(0)

@@ -2,7 +2,7 @@
 import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from tools.profile_spmm import build
+from tools._build import build
 from rvgp_b200._cabi import get_handle
 
 def main():

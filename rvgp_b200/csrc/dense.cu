@@ -281,7 +281,10 @@ colreduce_stage1(int64_t nrows, int ncols, const double* __restrict__ A, int64_t
     const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
     const int64_t r0 = (int64_t)blockIdx.x * RED_ROWS_PER_CTA;
     const int64_t r1 = (r0 + RED_ROWS_PER_CTA < nrows) ? r0 + RED_ROWS_PER_CTA : nrows;
-    for (int c0 = 0; c0 < ncols; c0 += 32) {
+    // one CTA per (row slab, 32-column panel): round 1 looped over the panels inside the CTA, which left a C2-sized reduction
+    // (35 k rows = 17 slabs) on 17 CTAs and made this kernel 14-20 % of the C2 kernel time (profiles/r02_launch_shares_c2.txt)
+    {
+        const int c0 = blockIdx.y * 32;
         const int c = c0 + cx;
         double s = 0.0;
         if (c < ncols) {
@@ -420,8 +423,9 @@ static int colreduce(Handle* h, int mode, int64_t nrows, int ncols, const double
     RVGP_REQUIRE(h, ncols >= 1 && nrows >= 0 && ws != nullptr, "colreduce: bad args");
     const int nslabs = cdiv(nrows, RED_ROWS_PER_CTA);
     if (nslabs > 0) {
-        if (mode == 0) colreduce_stage1<0><<<nslabs, 256, 0, h->stream>>>(nrows, ncols, A, lda, B, ldb, theta, ws);
-        else colreduce_stage1<1><<<nslabs, 256, 0, h->stream>>>(nrows, ncols, A, lda, B, ldb, theta, ws);
+        const dim3 grid(nslabs, cdiv(ncols, 32));
+        if (mode == 0) colreduce_stage1<0><<<grid, 256, 0, h->stream>>>(nrows, ncols, A, lda, B, ldb, theta, ws);
+        else colreduce_stage1<1><<<grid, 256, 0, h->stream>>>(nrows, ncols, A, lda, B, ldb, theta, ws);
         RVGP_LAUNCH_OK(h, "colreduce_stage1");
     }
     colreduce_stage2<<<cdiv(ncols, 128), 128, 0, h->stream>>>(nslabs, ncols, ws, out);

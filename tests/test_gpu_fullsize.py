@@ -90,3 +90,16 @@ def test_properties_200k():
     d = _props(200000, 128)
     # large problems take the filtered block Lanczos path (krylov.py); the invariants above are solver-independent
     assert "Lanczos" in str(d.stats["eig_L"].get("solver")) and "Lanczos" in str(d.stats["eig_Lc"].get("solver"))
+
+
+def test_properties_c4_size():
+    """The headline configuration itself (BASELINE.json configs[3]: 1M-point torus, k = 500): the reference cannot run it, so the
+    size-independent properties above are the parity statement at this size -- true residuals of all 500 + 500 Ritz pairs under
+    the stopping tolerance, orthonormality 1e-10, exactly paired Lc eigenvalues, L 1 = 0, R R^T = I, unit-norm smoothing,
+    K_diag == diag(K), dense == rank-k GP."""
+    d = _props(1000000, 500)
+    for name in ("eig_L", "eig_Lc"):
+        st = d.stats[name]
+        assert "Lanczos" in str(st.get("solver")) and st["converged"] and st["residual_max"] <= st["tol_abs"]
+        assert st["final_rr_outer"] == 1 and st["restarts"] == 0
+    torch.cuda.empty_cache()

@@ -94,3 +94,59 @@ def test_partition_balanced():
     b = partition_rows(g["indptr"], 8)
     nnz = np.diff(g["indptr"][b])
     assert len(b) == 9 and nnz.max() - nnz.min() <= 2 * np.diff(g["indptr"]).max()
+
+
+def _worker_gp_pieces(rank, world, port, q):
+    """The host-side pieces of the round-2 sharding: contiguous rank shares of an index list (row-sharded GP fit / transform),
+    the int32 row all-gather of the sharded geodesic stage, the bitwise OR of the per-rank flag words, and the data-parallel
+    identity the sharded fit rests on: sum over ranks of Phi_r^T [Phi_r y_r] == Phi^T [Phi y]."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from rvgp_b200.distributed import Comm
+        from rvgp_b200.main import _rank_chunk
+        comm = Comm()
+        for n_items in (0, 1, 7, 100, 101):
+            a, b, counts = _rank_chunk(n_items, comm)
+            assert sum(counts) == n_items and counts[rank] == b - a and a == sum(counts[:rank])
+            assert max(counts) - min(counts) <= 1
+        n, K = 103, 5
+        seq = torch.arange(n * (K + 1), dtype=torch.int32).reshape(n, K + 1)
+        s0, s1 = (n * rank) // world, (n * (rank + 1)) // world
+        rows = [(n * (r + 1)) // world - (n * r) // world for r in range(world)]
+        full = comm.allgather_rows(seq[s0:s1].clone(), rows)
+        assert full.dtype == torch.int32 and torch.equal(full, seq)
+        flags = torch.tensor([1 if rank == 0 else 4], dtype=torch.int32)
+        bits = torch.stack([(flags >> i) & 1 for i in range(3)]).reshape(3).to(torch.int32)
+        comm.allreduce_(bits)
+        word = int(((bits[0] > 0).to(torch.int32) | ((bits[1] > 0).to(torch.int32) << 1) | ((bits[2] > 0).to(torch.int32) << 2)).item())
+        assert word == (5 if world > 1 else 1)
+        rng = np.random.default_rng(0)
+        Phi, y = rng.normal(size=(200, 6)), rng.normal(size=(200, 1))
+        a, b, _ = _rank_chunk(200, comm)
+        XY = np.hstack([Phi[a:b], y[a:b]])
+        G = torch.from_numpy(XY.T @ XY)
+        comm.allreduce_(G)
+        XYf = np.hstack([Phi, y])
+        assert np.abs(G.numpy() - XYf.T @ XYf).max() < 1e-10
+        q.put((rank, "ok"))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put((rank, "FAIL: " + traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_gp_and_geodesic_host_pieces_gloo(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_gp_pieces, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] == "ok" for r in res), res

@@ -376,3 +376,49 @@ def test_projected_problem_device_path_matches_host_lapack(cplx):
     Gs[1] = Gs[0]; Gs[:, 1] = Gs[:, 0]                               # exactly singular -> shifted factor, flagged
     _, sh = E._cholqr_factor(Gs - 1e-9 * np.eye(m), dev)
     assert sh
+
+
+@pytest.mark.parametrize("kind,n,k", [("flat3torus", 6000, 40), ("sphere", 12000, 64), ("moebius", 8000, 48)])
+def test_krylov_solver_equals_chfsi_on_other_geometries(kind, n, k, monkeypatch):
+    """The filtered block Lanczos solver (krylov.py) against the subspace-iteration solver on geometries other than the benchmark
+    torus: a 3-manifold in R^6 (d = 3 blocks: REAL block mode on the gather kernel), a sphere (paired complex mode, exact
+    multiplicities 2l+1) and a Moebius strip (non-orientable: no paired mode).  Same eigenvalues to 1e-9 relative, same invariant
+    subspaces per cluster, true residuals under the tolerance."""
+    import RVGP
+    from tests.workloads import make_cloud
+    from tests.conftest import eigen_clusters, subspace_angle_max
+    X = make_cloud(kind, n, 0)
+    out = {}
+    for solver in ("chfsi", "krylov"):
+        monkeypatch.setenv("RVGP_EIGSOLVER", solver)
+        d = RVGP.create_data_object(X, n_eigenpairs=k, verbose=False)
+        assert ("Lanczos" in str(d.stats["eig_Lc"].get("solver"))) == (solver == "krylov")
+        for name in ("eig_L", "eig_Lc"):
+            st = d.stats[name]
+            assert st["converged"] and st["residual_max"] <= st["tol_abs"], (solver, name, st["residual_max"])
+        out[solver] = (d.evals_L.copy(), d.evals_Lc.copy(), d.evecs_L.copy(), d.evecs_Lc.copy(), d.stats["paired"], d.dim_man)
+    a, b = out["chfsi"], out["krylov"]
+    assert a[4] == b[4] and a[5] == b[5]
+    if kind == "moebius":
+        assert not a[4]
+    for ea, eb in ((a[0], b[0]), (a[1], b[1])):
+        assert np.abs(ea - eb).max() <= 1e-9 * np.abs(ea).max()
+    for ev, Ua, Ub in ((a[0], a[2], b[2]), (a[1], a[3], b[3])):
+        for s in eigen_clusters(ev, rtol=1e-6)[:-1]:
+            assert subspace_angle_max(Ua[:, s], Ub[:, s]) < 1e-6, (kind, s)
+
+
+def test_krylov_thick_restart_on_device():
+    """Thick restarts of the filtered block Lanczos solver on the GPU (a basis capacity far below what the run needs):
+    same eigenvalues as the golden ARPACK output of the unmodified reference."""
+    from rvgp_b200.krylov import krylov_eigenpairs
+    g = load_golden("sphere_n2000_k50")
+    A, S = _bsr_from_golden(g, "L")
+    hi = 2.0 * (np.diff(g["L_indptr"]).max() - 1)
+    ref = g["evals_L"]
+    st = {}
+    ev, U = krylov_eigenpairs(A, 40, hi, cut=1.3 * ref[49], lam_k=ref[39], block=16, cap_cols=144, stats=st)
+    assert st["restarts"] >= 1 and st["converged"]
+    np.testing.assert_allclose(ev.cpu().numpy(), ref[:40], rtol=1e-8, atol=1e-10)
+    Uh = U.cpu().numpy()
+    assert np.abs(S @ Uh - Uh * ev.cpu().numpy()).max() <= 1e-11 * hi

@@ -331,6 +331,8 @@ def krylov_eigenpairs(A, k, upper_bound, cut, lam_k, paired=False, tol=1e-12, bl
         # full pass against the whole basis: what is left along older blocks is rounding-level (full orthogonality has been
         # kept so far), so ONE classical Gram-Schmidt pass removes it without cancellation ("twice is enough", with the
         # first pass restricted to where the large components are)
+        # (It cannot be skipped: in the CPU emulation a full pass every 2nd block still converged identically, every 3rd block
+        # lost orthogonality and never converged -- the filtered operator amplifies the loss by ~e^4 per block.)
         C += ops.project_out(Vc, Wb)
         fresh_restart = False
         T[:cur, j0:cur] = C

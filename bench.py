@@ -10,7 +10,7 @@ One "step" = create_data_object + fit + transform on a synthetic point cloud (BA
   cpu_baseline   the oracle port of the reference's CPU path on a BOUNDED SAMPLE of the workload (reduced n and k);
            ``value`` is the time MEASURED on that sample, nothing is multiplied up
   --impl reference   ONE pass of the reference's CPU algorithm on the FULL workload under a wall-clock cap
-           (RVGP_REF_CAP_S, default 300 s): ``value`` = the seconds actually spent, ``capped`` says whether the pass
+           (RVGP_REF_CAP_S, default 420 s): ``value`` = the seconds actually spent, ``capped`` says whether the pass
            finished, and anything extrapolated lives in a separate, labelled ``extrapolated`` object.
 
 Nothing is retained between steps: every step's data object / model is dropped before the next one starts (round 1
@@ -438,7 +438,7 @@ def run_reference(args):
     if rank != 0:
         return
     wl = args.workload
-    cap = float(os.environ.get("RVGP_REF_CAP_S", "300"))
+    cap = float(os.environ.get("RVGP_REF_CAP_S", "420"))
     cores = _host_threads()
     t_all = time.perf_counter()
     passes = [reference_pass(wl, cap)]

@@ -257,7 +257,9 @@ class data:
 
         def solve_L(op, comm=None):
             """Smallest k_L eigenpairs of the scalar Laplacian (geometry.py:66-80 on L)."""
+            t_p = tick()
             lam = _coarse_spectrum(Xd, n_neighbors, 1.6 * k_L + 64) if kry_L else None
+            self.timings["eig_L_pilot"] = tick() - t_p
             if lam is None:
                 return smallest_eigenpairs(op, k_L, upper_bound=hi, tol=eig_tol, stats=st_L, comm=comm)
             J = max(1.5 * k_L, k_L + 64)

@@ -228,10 +228,12 @@ def krylov_eigenpairs(A, k, upper_bound, cut, lam_k, paired=False, tol=1e-12, bl
     kw = (k + 1) // 2 if paired else k                   # wanted pairs in the field the iteration works in
     nfield = Nglob // 2 if paired else Nglob
     hi = float(upper_bound)
+    t_bound0 = time.perf_counter()
     if _hi is not None:
         hi = _hi
     elif refine_bound:
         hi = min(hi, 1.01 * lanczos_upper_bound(A, comm=comm, h=h))
+    t_bound = time.perf_counter() - t_bound0
     lo = float(lower_bound)
     tol_abs = tol * float(upper_bound)
     cut = float(min(max(cut, 1.02 * lam_k), 0.5 * hi))
@@ -249,7 +251,8 @@ def krylov_eigenpairs(A, k, upper_bound, cut, lam_k, paired=False, tol=1e-12, bl
                    t_dense=0.0, t_host=0.0, spmm_bytes_fused=int(A.spmm_bytes(panel, fused=True)),
                    spmm_bytes_plain=int(A.spmm_bytes(panel, fused=False)), d=A.d, world=(comm.world if comm else 1), hi=hi,
                    hi_gershgorin=float(upper_bound), solver="filtered block Lanczos", paired=bool(paired), cut=cut, lam_k_est=float(lam_k),
-                   degree=d, blocks=0, restarts=0, checks=0, cap=cap))
+                   degree=d, blocks=0, restarts=0, checks=0, cap=cap, t_bound=t_bound))
+    t_loop0 = time.perf_counter()
 
     V = torch.empty((N, cap), dtype=torch.float64, device=dev)
     w0 = torch.empty((N, b), dtype=torch.float64, device=dev)
@@ -415,6 +418,9 @@ def krylov_eigenpairs(A, k, upper_bound, cut, lam_k, paired=False, tol=1e-12, bl
                 st["restarts"] += 1
     st["outer"] = st["blocks"]
     st["dense_tflop"] = ops.flops / 1e12
+    torch.cuda.synchronize(dev)
+    st["t_krylov_loop"] = time.perf_counter() - t_loop0
+    t_hand0 = time.perf_counter()
     if sharded_name:
         st["spmm_kernel"] = A.spmm_kernel_name
     if retry_cut is not None:
@@ -453,6 +459,8 @@ def krylov_eigenpairs(A, k, upper_bound, cut, lam_k, paired=False, tol=1e-12, bl
                        refine_bound=False, init_fn=start, hi_override=hi, m_exact=pk)
     for key in ("spmm_launches", "filter_launches", "filter_col_degrees", "t_filter", "t_dense", "t_host"):
         st[key] += st2.get(key, 0)
+    torch.cuda.synchronize(dev)
+    st["t_handoff"] = time.perf_counter() - t_hand0
     st["final_rr_outer"] = st2.get("outer")
     st["m_final"] = st2.get("m")
     st["residual_max"], st["converged"], st["tol_abs"] = st2["residual_max"], st2["converged"], st2["tol_abs"]

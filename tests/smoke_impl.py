@@ -22,4 +22,18 @@ def run_smoke():
     assert np.abs(Y.cpu().numpy() - Lc @ X).max() < 1e-12
     ev, U = smallest_eigenpairs(A, 20, upper_bound=2.0 * (np.diff(g["indptr"]).max() - 1))
     np.testing.assert_allclose(ev.cpu().numpy(), ev_ref, rtol=1e-8, atol=1e-9)
-    print("smoke ok: SpMM + eigensolver match the oracle; evals[:4] =", ev[:4].cpu().numpy())
+    # round 2: the scalar Laplacian on the FP64-MMA kernel (pattern mode) and the filtered block Lanczos solver, same oracle
+    gs = load_golden("sphere_n2000_k50")
+    ns = gs["X"].shape[0]
+    Ls = O.laplacian(gs["indptr"], gs["indices"])
+    AL = BsrMatrix(ns, 1, torch.from_numpy(gs["indptr"]).to(dev), torch.from_numpy(gs["indices"]).to(dev), None)
+    assert AL.enable_mma_pattern() is not None
+    Xs = np.random.default_rng(1).normal(size=(ns, 64))
+    Ys = AL.spmm_pattern(torch.from_numpy(Xs).to(dev), torch.empty((ns, 64), dtype=torch.float64, device=dev))
+    assert np.abs(Ys.cpu().numpy() - Ls @ Xs).max() < 1e-12
+    from rvgp_b200.krylov import krylov_eigenpairs
+    evL_ref, _ = O.spectrum(Ls, 60)
+    his = 2.0 * (np.diff(gs["indptr"]).max() - 1)
+    evk, _ = krylov_eigenpairs(AL, 40, his, cut=1.05 * evL_ref[59], lam_k=evL_ref[39], block=16)
+    np.testing.assert_allclose(evk.cpu().numpy(), evL_ref[:40], rtol=1e-8, atol=1e-9)
+    print("smoke ok: SpMM (gather + MMA pattern) and both eigensolvers match the oracle; evals[:4] =", ev[:4].cpu().numpy())

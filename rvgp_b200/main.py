@@ -324,7 +324,6 @@ def train_gp(data,
         comm = Comm()
         if comm.world > 1:
             a, b, _ = _rank_chunk(len(tr), comm)
-            tr_all, te_all = tr, te
             tr = tr[a:b]
             a2, b2, _ = _rank_chunk(len(te), comm)
             te = te[a2:b2]

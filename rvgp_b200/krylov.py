@@ -152,20 +152,21 @@ class FieldOps:
         for _pass in range(3):
             G = self.gram_self(src)
             t0 = time.perf_counter()
-            with _lapack_ctx():
-                shifted = False
-                try:
-                    R = np.linalg.cholesky(G).conj().T
-                except np.linalg.LinAlgError:
-                    shifted = True
-                    shift = 1e-13 * nb * max(float(np.abs(np.diag(G)).max()), 1e-300)
-                    while True:
-                        try:
-                            R = np.linalg.cholesky(G + shift * np.eye(nb)).conj().T
-                            break
-                        except np.linalg.LinAlgError:
-                            shift *= 100.0
-                Rinv = _tri_inv_upper(R)
+            # (the caller holds ONE _lapack_ctx around the whole block loop: entering / leaving the BLAS thread limit costs
+            # ~150 us, more than this b x b factorisation itself)
+            shifted = False
+            try:
+                R = np.linalg.cholesky(G).conj().T
+            except np.linalg.LinAlgError:
+                shifted = True
+                shift = 1e-13 * nb * max(float(np.abs(np.diag(G)).max()), 1e-300)
+                while True:
+                    try:
+                        R = np.linalg.cholesky(G + shift * np.eye(nb)).conj().T
+                        break
+                    except np.linalg.LinAlgError:
+                        shift *= 100.0
+            Rinv = _tri_inv_small(R)
             st["t_host"] += time.perf_counter() - t0
             dst = out if src is not out else self._swap(out)
             self.right_multiply(src, Rinv, dst)
@@ -187,6 +188,15 @@ import os as _os
 _HOST_EIGH = _os.environ.get("RVGP_HOST_EIGH", "0") == "1"
 
 
+def _tri_inv_small(R):
+    """Inverse of a small upper-triangular matrix (LAPACK ?trtri: 70 us for 64 x 64 against 270 us for a triangular solve with I)."""
+    import scipy.linalg.lapack as lp
+    Ri, info = (lp.ztrtri(R) if np.iscomplexobj(R) else lp.dtrtri(R))
+    if info != 0:
+        return _tri_inv_upper(R)
+    return np.triu(Ri)
+
+
 def _filter_degree(cut, lam_k, hi, lo, nats):
     e, c = 0.5 * (hi - cut), 0.5 * (hi + cut)
     gk = math.acosh(max((c - lam_k) / e, 1.0 + 1e-12))
@@ -204,7 +214,14 @@ def _rho_inverse(theta, cut, hi, lo, d):
     return c - e * math.cosh(math.acosh(y) / d)
 
 
-def krylov_eigenpairs(A, k, upper_bound, cut, lam_k, paired=False, tol=1e-12, block=64, nats=4.0, seed=0, stats=None, comm=None,
+def krylov_eigenpairs(*args, **kwargs):
+    """Smallest k eigenpairs by filtered block Lanczos (see _krylov_eigenpairs for the arguments).  ONE BLAS thread limit is held
+    for the whole run: the b x b host factorisations of the block loop are far cheaper than entering / leaving the limit."""
+    with _lapack_ctx():
+        return _krylov_eigenpairs(*args, **kwargs)
+
+
+def _krylov_eigenpairs(A, k, upper_bound, cut, lam_k, paired=False, tol=1e-12, block=64, nats=4.0, seed=0, stats=None, comm=None,
                       refine_bound=True, lower_bound=0.0, cap_cols=None, max_blocks=400, init_fn=None, verbose=False,
                       _depth=0, _hi=None):
     """Smallest k eigenpairs of the symmetric PSD operator ``A`` (BsrMatrix / ShardedBsr) by filtered block Lanczos.
@@ -426,7 +443,7 @@ def krylov_eigenpairs(A, k, upper_bound, cut, lam_k, paired=False, tol=1e-12, bl
     if retry_cut is not None:
         del V, w0, w1, w2, Wb, ops
         prev = dict(st)
-        out = krylov_eigenpairs(A, k, upper_bound, retry_cut, retry_cut / 1.5, paired=paired, tol=tol, block=block, nats=nats,
+        out = _krylov_eigenpairs(A, k, upper_bound, retry_cut, retry_cut / 1.5, paired=paired, tol=tol, block=block, nats=nats,
                                 seed=seed, stats=st, comm=comm, lower_bound=lower_bound, cap_cols=cap_cols, max_blocks=max_blocks,
                                 init_fn=init_fn, verbose=verbose, _depth=_depth + 1, _hi=hi)
         for key in ("spmm_launches", "filter_launches", "filter_col_degrees", "t_filter", "t_dense", "t_host", "blocks", "checks"):

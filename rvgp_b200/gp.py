@@ -100,6 +100,7 @@ class DeviceGPR:
         Gh = Gd.cpu().numpy()
         Gh = 0.5 * (Gh + Gh.T)
         self.G, self.b, self.yy = Gh[:k, :k].copy(), Gh[:k, k].copy(), float(Gh[k, k])
+        self._Gdiag = np.diag(self.G).copy()
         self._small = k <= 64
         if not self._small:
             # K15b: the whole evaluation is one C call on resident data (rvgp_gp_lowrank_eval_f64); per evaluation the host
@@ -175,7 +176,7 @@ class DeviceGPR:
         c = rs * z
         Gc = self.G @ c
         u = (self.b - Gc / noise) / noise
-        wdiag = (np.diag(self.G) - qs_h / noise) / noise
+        wdiag = (self._Gdiag - qs_h / noise) / noise
         dS = 0.5 * u ** 2 - 0.5 * wdiag
         aa = (self.yy - 2.0 * (self.b @ c) / noise + (c @ Gc) / noise ** 2) / noise ** 2
         tr_inv = (M - (S * wdiag).sum()) / noise

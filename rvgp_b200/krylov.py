@@ -178,10 +178,10 @@ class FieldOps:
             src = out
             Rtot = R @ Rtot
             st["cholqr_passes_krylov"] = st.get("cholqr_passes_krylov", 0) + 1
-            # One pass suffices when the block is well conditioned: the departure from orthonormality of CholeskyQR is
-            # ~cond(W)^2 times the rounding error of the Gram product.  The residual blocks of the filtered Lanczos process are
-            # (measured at C4: diag(R) ratios <= 3.6), so the second pass is only taken for cond_1(R) >= 20 or after a shift.
-            if not shifted and (_pass >= 1 or kappa1 < 20.0):
+            # Always two passes (CholeskyQR2).  A single pass for well-conditioned blocks was measured in round 2: the residual
+            # blocks are well conditioned (diag(R) ratios <= 3.6, cond_1(R) 20-200 at C4), but a rule that is safe for the
+            # Lanczos relation (cond_1(R) < 20) only skipped a quarter of the second passes, ~10 ms of the 4.4 s step.
+            if _pass >= 1 and not shifted:
                 break
         return Rtot
 

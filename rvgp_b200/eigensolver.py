@@ -358,7 +358,7 @@ class _Dense:
 
 def smallest_eigenpairs(A, k, upper_bound, lower_bound=0.0, tol=1e-12, nex=None, seed=0, max_outer=80,
                         cond_max=1e6, deg0=20, panel=None, stats=None, verbose=False, comm=None,
-                        refine_bound=True, init_fn=None, hi_override=None, m_exact=None):
+                        refine_bound=True, init_fn=None, hi_override=None, m_exact=None, orthonormal_start=False):
     """Smallest k eigenpairs of the symmetric PSD BsrMatrix ``A``.
 
     upper_bound: a rigorous upper bound of the spectrum (2 * max degree for (connection) Laplacians).
@@ -457,8 +457,11 @@ def smallest_eigenpairs(A, k, upper_bound, lower_bound=0.0, tol=1e-12, nex=None,
         # ---- orthonormalise: column scaling + Cholesky-QR, then Rayleigh-Ritz with the second
         #      Cholesky folded into the projected problem ---------------------------------------------
         # CholeskyQR passes until one succeeds WITHOUT a diagonal shift (shifted CholeskyQR3: a failed /
-        # shifted pass still reduces cond(V) by orders of magnitude, so the next pass is safe)
-        for _pass in range(4):
+        # shifted pass still reduces cond(V) by orders of magnitude, so the next pass is safe).
+        # orthonormal_start (hand-over from krylov.py): the start block is already orthonormal to ~1e-13 and is not filtered in
+        # the first sweep, so the explicit pass is skipped there -- the Rayleigh-Ritz below solves the GENERALISED problem with
+        # G = V^T V anyway (2 Gram products and 1 block multiply less: ~40 % of the hand-over)
+        for _pass in range(0 if (orthonormal_start and it == 0) else 4):
             nrm = dense.coldot(V, V)
             inv = torch.rsqrt(nrm)
             dense.colscale(V, inv)
@@ -714,7 +717,7 @@ def _chol_upper_shifted_c(G):
 
 def smallest_eigenpairs_paired(A, k, upper_bound, lower_bound=0.0, tol=1e-12, nex=None, seed=0, max_outer=80,
                                cond_max=1e6, deg0=20, panel=None, stats=None, verbose=False, comm=None,
-                               refine_bound=True, init_fn=None, hi_override=None, m_exact=None):
+                               refine_bound=True, init_fn=None, hi_override=None, m_exact=None, orthonormal_start=False):
     """Smallest k eigenpairs of a d = 2 block matrix ``A`` that commutes with J (all blocks scaled rotations), through its
     complex-Hermitian form.  Same contract as ``smallest_eigenpairs``: returns (evals (k,), evecs (N, k)) with unit-norm
     columns, ascending; columns 2j and 2j+1 are (v_j, J v_j) of the j-th complex eigenpair."""
@@ -825,7 +828,7 @@ def smallest_eigenpairs_paired(A, k, upper_bound, lower_bound=0.0, tol=1e-12, ne
         _nvtx.pop()
         _nvtx.push("eig:orthonormalise+rayleigh_ritz")
         # ---- complex CholeskyQR (shifted CholeskyQR3 on breakdown), then Rayleigh-Ritz ---------------------------------
-        for _pass in range(4):
+        for _pass in range(0 if (orthonormal_start and it == 0) else 4):
             nrm = dense.coldot(V, V)
             inv = torch.rsqrt(nrm)
             dense.colscale(V, inv)

@@ -171,11 +171,16 @@ class FieldOps:
             if _pass == 0:
                 st["cholqr_cond1_max"] = max(st.get("cholqr_cond1_max", 1.0), kappa1)
             st["t_host"] += time.perf_counter() - t0
-            dst = out if src is not out else self._swap(out)
+            # ping-pong: pass 0 writes the scratch panel, pass 1 writes `out` (no copy); a third pass (after a shift) goes
+            # through the scratch panel and is copied
+            if _pass == 0:
+                dst = self._swap(out)
+            elif _pass == 1:
+                dst = out
+            else:
+                dst = self._swap(out) if src is out else out
             self.right_multiply(src, Rinv, dst)
-            if dst is not out:
-                out.copy_(dst)
-            src = out
+            src = dst
             Rtot = R @ Rtot
             st["cholqr_passes_krylov"] = st.get("cholqr_passes_krylov", 0) + 1
             # Always two passes (CholeskyQR2).  A single pass for well-conditioned blocks was measured in round 2: the residual
@@ -183,6 +188,8 @@ class FieldOps:
             # Lanczos relation (cond_1(R) < 20) only skipped a quarter of the second passes, ~10 ms of the 4.4 s step.
             if _pass >= 1 and not shifted:
                 break
+        if src is not out:
+            out.copy_(src)
         return Rtot
 
     def _swap(self, like):
@@ -480,7 +487,7 @@ def _krylov_eigenpairs(A, k, upper_bound, cut, lam_k, paired=False, tol=1e-12, b
     fin = smallest_eigenpairs_paired if paired else smallest_eigenpairs
     X = None
     evals, evecs = fin(A, k, upper_bound, lower_bound=lower_bound, tol=tol, seed=seed + 1, deg0=0, panel=b, stats=st2, comm=comm,
-                       refine_bound=False, init_fn=start, hi_override=hi, m_exact=pk)
+                       refine_bound=False, init_fn=start, hi_override=hi, m_exact=pk, orthonormal_start=True)
     for key in ("spmm_launches", "filter_launches", "filter_col_degrees", "t_filter", "t_dense", "t_host"):
         st[key] += st2.get(key, 0)
     torch.cuda.synchronize(dev)

@@ -32,6 +32,7 @@ struct Handle {
     unsigned long long gp_graph_launches;
     cudaStream_t gp_stream;       // blocking side stream used when the handle follows the legacy default stream (not capturable)
     int gp_graph_off;             // 1: capture failed once, run eagerly from now on (or rvgp_set_option("gp_graph", 0))
+    int dgemm_pipe_attr;          // 1 once the pipelined DGEMM's dynamic shared memory limit is raised on this handle's device
 };
 
 inline Handle* H(rvgp_handle_t h) { return reinterpret_cast<Handle*>(h); }

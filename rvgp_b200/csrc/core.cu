@@ -19,7 +19,7 @@ extern "C" int rvgp_create(int device, rvgp_handle_t* out) {
     h->rowlist = nullptr;
     h->nlist = 0;
     h->spmm_stage = 0;   // measured: no gain (tools/profile_stage.py); value loads are not the limiter
-    h->dgemm_dmma = 1;   // measured on B200: 17 vs 14 TFLOP/s for the tall-skinny Gram (tools/ncu_dgemm.py)
+    h->dgemm_dmma = 2;   // 0 DFMA register tile, 1 DMMA (17 vs 14 TFLOP/s on the tall-skinny Gram, tools/ncu_dgemm.py), 2 cp.async-pipelined DMMA
     h->mma_gpw = 0;
     // measured on B200 at C4 size (tools/profile_mma.py, profiles/r01_spmm_mma_sweep.txt): 256-thread CTAs x 2, register ring
     // of 2 k-steps, persistent warp-strided schedule, streams evict-first in L2, L2 prefetch one group ahead
@@ -31,6 +31,7 @@ extern "C" int rvgp_create(int device, rvgp_handle_t* out) {
     h->gp_graph_launches = 0;
     h->gp_stream = nullptr;
     h->gp_graph_off = 0;
+    h->dgemm_pipe_attr = 0;
     for (int i = 0; i < 6; ++i) h->gp_graph_key[i] = nullptr;
     h->last_error[0] = 0;
     cudaDeviceProp prop;

@@ -257,6 +257,132 @@ dgemm_dmma_kernel(int M, int N, int64_t K, double alpha, const double* __restric
     }
 }
 
+// ---- pipelined DMMA variant (round 2): same CTA / warp tiling as dgemm_dmma_kernel, operands streamed global -> shared by
+// cp.async (16 B) through a 3-stage ring, one __syncthreads per k-tile.  The register-staged kernel above sits at ~17 TFLOP/s
+// on the eigensolver's two skinny shapes with long-scoreboard as its first stall (profiles/r01_dgemm_dmma_summary.txt: every
+// warp waits for its own global loads before it can store the tile); here the loads of tile kt+2 are in flight while tile kt
+// is consumed and no warp ever waits on a register.  Layouts: B is N-major (k rows of n-contiguous doubles, the only layout
+// the eigensolver uses); A is M-major (Gram V^T W: k rows of m-contiguous doubles) or K-major (update W -= V C: m rows of
+// k-contiguous doubles, kept in that orientation in shared memory).  Row strides = 4 (mod 16) doubles keep the
+// (gid, tig) fragment reads conflict-free in both orientations.  Needs 16-byte aligned operands and even extents (dispatch).
+constexpr int PST = 3;
+constexpr int PA_M = BK * (BM + DPAD);
+constexpr int PA_K = BM * (BK + DPAD);
+constexpr int PA_SZ = PA_K > PA_M ? PA_K : PA_M;
+constexpr int PB_SZ = BK * (DBN + DPAD);
+constexpr int PSTAGE = PA_SZ + PB_SZ;
+constexpr size_t PIPE_SMEM = (size_t)PST * PSTAGE * sizeof(double);
+
+__device__ __forceinline__ void cp_async16(double* smem, const double* gmem, bool ok) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    const int sz = ok ? 16 : 0;                       // src-size 0: the 16 bytes are zero-filled, nothing is read
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(s), "l"(gmem), "r"(sz) : "memory");
+}
+
+template <bool A_KMAJOR>
+__global__ void __launch_bounds__(256, 2)
+dgemm_dmma_pipe_kernel(int M, int N, int64_t K, double alpha, const double* __restrict__ A, int64_t lda,
+                       const double* __restrict__ B, int64_t ldb, double* __restrict__ C, int64_t ldc, int split_k,
+                       double* __restrict__ ws, double beta, int lower_only) {
+    if (lower_only && blockIdx.x * DBN > blockIdx.y * BM + (BM - 1)) return;
+    extern __shared__ __align__(16) double psm[];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int wm = warp >> 1, wn = warp & 1;
+    const int gid = lane >> 2, tig = lane & 3;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * DBN;
+    const int64_t ktiles = (K + BK - 1) / BK;
+    const int64_t tiles_per = (ktiles + split_k - 1) / split_k;
+    const int64_t kt0 = (int64_t)blockIdx.z * tiles_per;
+    const int64_t kt1 = (kt0 + tiles_per < ktiles) ? kt0 + tiles_per : ktiles;
+    const int nk = kt1 > kt0 ? (int)(kt1 - kt0) : 0;
+
+    auto issue = [&](int64_t kt, int st) {
+        double* As = psm + st * PSTAGE;
+        double* Bs = As + PA_SZ;
+        const int64_t k0 = kt * BK;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int c = t + 256 * r;
+            if (A_KMAJOR) {
+                const int m = c >> 3, kp = (c & 7) * 2;
+                const int gi = m0 + m;
+                const int64_t gk = k0 + kp;
+                const bool ok = (gi < M) && (gk < K);
+                cp_async16(As + m * (BK + DPAD) + kp, ok ? A + (int64_t)gi * lda + gk : A, ok);
+            } else {
+                const int k = c >> 6, mp = (c & 63) * 2;
+                const int gi = m0 + mp;
+                const int64_t gk = k0 + k;
+                const bool ok = (gi < M) && (gk < K);
+                cp_async16(As + k * (BM + DPAD) + mp, ok ? A + gk * lda + gi : A, ok);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int c = t + 256 * r;
+            const int k = c >> 5, np = (c & 31) * 2;
+            const int gj = n0 + np;
+            const int64_t gk = k0 + k;
+            const bool ok = (gj < N) && (gk < K);
+            cp_async16(Bs + k * (DBN + DPAD) + np, ok ? B + gk * ldb + gj : B, ok);
+        }
+    };
+
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+#pragma unroll
+    for (int s = 0; s < PST - 1; ++s) {
+        if (s < nk) issue(kt0 + s, s);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (int it = 0; it < nk; ++it) {
+        asm volatile("cp.async.wait_group %0;" :: "n"(PST - 2) : "memory");
+        __syncthreads();                               // tile `it` visible to all; everyone is done with tile it-1's stage
+        if (it + PST - 1 < nk) issue(kt0 + it + PST - 1, (it + PST - 1) % PST);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        const double* As = psm + (it % PST) * PSTAGE;
+        const double* Bs = As + PA_SZ;
+#pragma unroll
+        for (int k4 = 0; k4 < BK; k4 += 4) {
+            double a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                a[i] = A_KMAJOR ? As[(wm * 32 + i * 8 + gid) * (BK + DPAD) + k4 + tig] : As[(k4 + tig) * (BM + DPAD) + wm * 32 + i * 8 + gid];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[(k4 + tig) * (DBN + DPAD) + wn * 32 + j * 8 + gid];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+
+    double* out = C;
+    int64_t ldo = ldc;
+    double sc = alpha;
+    if (split_k > 1) { out = ws + (int64_t)blockIdx.z * M * N; ldo = N; sc = 1.0; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int gi = m0 + wm * 32 + i * 8 + gid;
+        if (gi >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gj = n0 + wn * 32 + j * 8 + 2 * tig;
+            if (gj + 1 < N) {                          // N is even (dispatch): the pair is in range together
+                double2 v = make_double2(sc * acc[i][j][0], sc * acc[i][j][1]);
+                double2* po = reinterpret_cast<double2*>(out + (int64_t)gi * ldo + gj);
+                if (beta != 0.0 && split_k == 1) { const double2 o = *po; v.x = fma(beta, o.x, v.x); v.y = fma(beta, o.y, v.y); }
+                *po = v;
+            }
+        }
+    }
+}
+
 __global__ void splitk_reduce_kernel(int M, int N, int split_k, double alpha, const double* __restrict__ ws,
                                      double* __restrict__ C, int64_t ldc, double beta) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -365,7 +491,21 @@ int dgemm_launch(Handle* h, int m, int n, int64_t k, double alpha, const double*
     RVGP_REQUIRE(h, m >= 0 && n >= 0 && k >= 0 && split_k >= 1, "dgemm: bad sizes");
     RVGP_REQUIRE(h, split_k == 1 || workspace != nullptr, "dgemm: split_k > 1 needs a workspace");
     if (m == 0 || n == 0) return RVGP_OK;
-    if (h->dgemm_dmma) {
+    // pipelined kernel: needs 16-byte aligned 2-element chunks along the contiguous index of every operand (and of C / ws)
+    const bool pipe_ok = h->dgemm_dmma >= 2 && scale_k == nullptr && !b_kmajor && (n % 2 == 0) && (lda % 2 == 0) &&
+                         (ldb % 2 == 0) && (ldc % 2 == 0) && (a_kmajor ? (k % 2 == 0) : (m % 2 == 0)) &&
+                         ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C) |
+                           reinterpret_cast<uintptr_t>(workspace)) % 16 == 0);
+    if (pipe_ok) {
+        if (!h->dgemm_pipe_attr) {
+            RVGP_CUDA_OK(h, cudaFuncSetAttribute(dgemm_dmma_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_SMEM));
+            RVGP_CUDA_OK(h, cudaFuncSetAttribute(dgemm_dmma_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_SMEM));
+            h->dgemm_pipe_attr = 1;
+        }
+        dim3 grid(cdiv(n, DBN), cdiv(m, BM), split_k);
+        if (a_kmajor) dgemm_dmma_pipe_kernel<true><<<grid, 256, PIPE_SMEM, h->stream>>>(m, n, k, alpha, A, lda, B, ldb, C, ldc, split_k, workspace, beta, lower_only);
+        else dgemm_dmma_pipe_kernel<false><<<grid, 256, PIPE_SMEM, h->stream>>>(m, n, k, alpha, A, lda, B, ldb, C, ldc, split_k, workspace, beta, lower_only);
+    } else if (h->dgemm_dmma) {
         dim3 grid(cdiv(n, DBN), cdiv(m, BM), split_k);
 #define RVGP_GEMM(AK, BKM) do { if (scale_k) dgemm_dmma_kernel<AK, BKM, true><<<grid, 256, 0, h->stream>>>(m, n, k, alpha, A, lda, B, ldb, scale_k, C, ldc, split_k, workspace, beta, lower_only); else dgemm_dmma_kernel<AK, BKM, false><<<grid, 256, 0, h->stream>>>(m, n, k, alpha, A, lda, B, ldb, scale_k, C, ldc, split_k, workspace, beta, lower_only); } while (0)
         if (a_kmajor && b_kmajor) RVGP_GEMM(true, true);

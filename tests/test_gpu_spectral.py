@@ -105,7 +105,54 @@ def test_dgemm_layouts(shape, dmma):
                 err = np.abs(C[:, :n].cpu().numpy() - ref).max()
                 assert err <= 1e-13 * k ** 0.5 * max(1, np.abs(ref).max()), (akm, bkm, split, err)
                 assert C[:, n:].abs().max().item() == 0.0
-    h.set_option("dgemm_dmma", 0)
+    h.set_option("dgemm_dmma", 2)                                   # the handle is shared: back to the default
+
+
+@pytest.mark.parametrize("shape", [(2, 2, 2), (64, 64, 100001), (130, 66, 4098), (704, 64, 50000), (50001 * 2, 64, 192),
+                                   (3000, 130, 66), (256, 256, 70000)])
+def test_dgemm_pipelined_kernel(shape):
+    """The cp.async-pipelined DMMA kernel (dgemm_dmma = 2: even extents, 16-byte aligned operands, N-major B) against numpy and
+    against the register-staged kernel; ragged M / N / K tails, split-K, the accumulate entry and the lower-triangle entry."""
+    from rvgp_b200.eigensolver import _dgemm
+    from rvgp_b200._cabi import get_handle, I64
+    m, n, k = shape
+    h = get_handle(0)
+    rng = np.random.default_rng(1)
+    A = rng.normal(size=(m, k)); B = rng.normal(size=(k, n)); C0 = rng.normal(size=(m, n))
+    ref = A @ B
+    tol = 1e-13 * k ** 0.5 * max(1, np.abs(ref).max())
+    Bd = torch.from_numpy(B).to(_dev())
+    try:
+        for akm in (0, 1):
+            Ad = torch.from_numpy(np.ascontiguousarray(A if akm else A.T)).to(_dev())
+            for split in (1, 3):
+                outs = []
+                for mode in (2, 1):
+                    h.set_option("dgemm_dmma", mode)
+                    C = torch.zeros((m, n + 2), dtype=torch.float64, device=_dev())
+                    ws = torch.empty(split * m * n, dtype=torch.float64, device=_dev())
+                    l0 = h.launches
+                    _dgemm(h, m, n, k, Ad, Ad.stride(0), akm, Bd, Bd.stride(0), 0, C, C.stride(0), alpha=0.5, split_k=split, ws=ws)
+                    assert h.launches - l0 == (2 if split > 1 else 1)
+                    assert C[:, n:].abs().max().item() == 0.0
+                    outs.append(C[:, :n].cpu().numpy())
+                    assert np.abs(outs[-1] - 0.5 * ref).max() <= tol, (akm, split, mode)
+                assert np.abs(outs[0] - outs[1]).max() <= tol
+            # accumulate: C = -A B + C  (the eigensolver's W -= V C update)
+            h.set_option("dgemm_dmma", 2)
+            C = torch.from_numpy(C0).to(_dev())
+            h.call("rvgp_dgemm_acc_f64", int(m), int(n), I64(k), -1.0, Ad, I64(Ad.stride(0)), int(akm), Bd, I64(n), 0, 1.0, C, I64(n))
+            assert np.abs(C.cpu().numpy() - (C0 - ref)).max() <= tol
+        if m == n:                                                  # SYRK-style entry: lower-triangle tiles only
+            Ad = torch.from_numpy(np.ascontiguousarray(A.T)).to(_dev())
+            G = torch.full((m, m), 7.0, dtype=torch.float64, device=_dev())
+            ws = torch.empty(3 * m * m, dtype=torch.float64, device=_dev())
+            h.call("rvgp_dgemm_lower_f64", int(m), int(m), I64(k), 1.0, Ad, I64(m), 0, Ad, I64(m), 0, G, I64(m), 3, ws)
+            Gh = G.cpu().numpy(); full = A @ A.T
+            il = np.tril_indices(m)
+            assert np.abs(Gh[il] - full[il]).max() <= 1e-13 * k ** 0.5 * np.abs(full).max()
+    finally:
+        h.set_option("dgemm_dmma", 2)
 
 
 def test_column_reductions_and_utils():

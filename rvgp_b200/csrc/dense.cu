@@ -383,6 +383,99 @@ dgemm_dmma_pipe_kernel(int M, int N, int64_t K, double alpha, const double* __re
     }
 }
 
+// ---- small-shape DMMA variant: 32 x 32 x 32 CTA tile, 4 warps (2 x 2), warp tile 16 x 16 --------------------------------------
+// The k x k (k ~ 500) Cholesky panels and solves of the rank-k GP evaluation are a few hundred rows by 64..256 columns: with the
+// 128 x 64 tile they occupy 4-12 of the 148 SMs and each CTA then needs >= 17 us for a K = 256 product (one SM's FP64 rate).
+// Sixteen times more, smaller CTAs put the same product on 16 x as many SMs; operands stay in the orientation they have in
+// memory (row stride 36 = 4 mod 16 doubles: conflict-free stores and (gid, tig) fragment reads in both orientations).
+constexpr int SBM = 32, SBN = 32, SBK = 32, SLD = SBK + 4;
+
+template <bool A_KMAJOR, bool B_KMAJOR>
+__global__ void __launch_bounds__(128)
+dgemm_small_kernel(int M, int N, int64_t K, double alpha, const double* __restrict__ A, int64_t lda,
+                   const double* __restrict__ B, int64_t ldb, double* __restrict__ C, int64_t ldc, double beta, int lower_only) {
+    if (lower_only && blockIdx.x * SBN > blockIdx.y * SBM + (SBM - 1)) return;
+    __shared__ double As[SBK * SLD];      // K-major source: [m][k], otherwise [k][m]
+    __shared__ double Bs[SBK * SLD];      // K-major source: [n][k], otherwise [k][n]
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int wm = warp >> 1, wn = warp & 1;
+    const int gid = lane >> 2, tig = lane & 3;
+    const int m0 = blockIdx.y * SBM, n0 = blockIdx.x * SBN;
+    const int64_t ktiles = (K + SBK - 1) / SBK;
+    double acc[2][2][2] = {};
+    double ra[8], rb[8];
+    // element (fast index f = lane, slow index s = warp + 4 r): for a K-major operand f runs along k, otherwise along m / n
+    auto load_tiles = [&](int64_t kt) {
+        const int64_t k0 = kt * SBK;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int f = lane, sl = warp + 4 * r;
+            {
+                const int64_t gk = k0 + (A_KMAJOR ? f : sl);
+                const int gi = m0 + (A_KMAJOR ? sl : f);
+                const bool ok = (gi < M) && (gk < K);
+                const double* pa = A_KMAJOR ? (A + (int64_t)(ok ? gi : 0) * lda + (ok ? gk : 0)) : (A + (ok ? gk : 0) * lda + (ok ? gi : 0));
+                ra[r] = ok ? __ldg(pa) : 0.0;
+            }
+            {
+                const int64_t gk = k0 + (B_KMAJOR ? f : sl);
+                const int gj = n0 + (B_KMAJOR ? sl : f);
+                const bool ok = (gj < N) && (gk < K);
+                const double* pb = B_KMAJOR ? (B + (int64_t)(ok ? gj : 0) * ldb + (ok ? gk : 0)) : (B + (ok ? gk : 0) * ldb + (ok ? gj : 0));
+                rb[r] = ok ? __ldg(pb) : 0.0;
+            }
+        }
+    };
+    auto store_tiles = [&]() {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            As[(warp + 4 * r) * SLD + lane] = ra[r];
+            Bs[(warp + 4 * r) * SLD + lane] = rb[r];
+        }
+    };
+    if (ktiles > 0) load_tiles(0);
+    for (int64_t kt = 0; kt < ktiles; ++kt) {
+        store_tiles();
+        __syncthreads();
+        if (kt + 1 < ktiles) load_tiles(kt + 1);
+#pragma unroll
+        for (int k4 = 0; k4 < SBK; k4 += 4) {
+            double a[2], b[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int m = wm * 16 + i * 8 + gid;
+                a[i] = A_KMAJOR ? As[m * SLD + k4 + tig] : As[(k4 + tig) * SLD + m];
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int n = wn * 16 + j * 8 + gid;
+                b[j] = B_KMAJOR ? Bs[n * SLD + k4 + tig] : Bs[(k4 + tig) * SLD + n];
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int gi = m0 + wm * 16 + i * 8 + gid;
+        if (gi >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int gj = n0 + wn * 16 + j * 8 + 2 * tig + c;
+                if (gj < N) {
+                    double v = alpha * acc[i][j][c];
+                    if (beta != 0.0) v = fma(beta, C[(int64_t)gi * ldc + gj], v);
+                    C[(int64_t)gi * ldc + gj] = v;
+                }
+            }
+    }
+}
+
 __global__ void splitk_reduce_kernel(int M, int N, int split_k, double alpha, const double* __restrict__ ws,
                                      double* __restrict__ C, int64_t ldc, double beta) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -491,12 +584,27 @@ int dgemm_launch(Handle* h, int m, int n, int64_t k, double alpha, const double*
     RVGP_REQUIRE(h, m >= 0 && n >= 0 && k >= 0 && split_k >= 1, "dgemm: bad sizes");
     RVGP_REQUIRE(h, split_k == 1 || workspace != nullptr, "dgemm: split_k > 1 needs a workspace");
     if (m == 0 || n == 0) return RVGP_OK;
+    // bit 1 of lower_only: C aliases A (in-place right-multiplication of a row panel).  Safe only when ONE CTA column covers all
+    // of n, so that a CTA has consumed every element of its own rows before it stores them: the 128 x 64-tile kernel, n <= 64.
+    const bool in_place = (lower_only & 2) != 0;
+    lower_only &= 1;
+    RVGP_REQUIRE(h, !in_place || (n <= DBN && split_k == 1), "dgemm: in-place needs n <= 64 and no split-K");
     // pipelined kernel: needs 16-byte aligned 2-element chunks along the contiguous index of every operand (and of C / ws)
-    const bool pipe_ok = h->dgemm_dmma >= 2 && scale_k == nullptr && !b_kmajor && (n % 2 == 0) && (lda % 2 == 0) &&
+    const bool pipe_ok = !in_place && h->dgemm_dmma >= 2 && scale_k == nullptr && !b_kmajor && (n % 2 == 0) && (lda % 2 == 0) &&
                          (ldb % 2 == 0) && (ldc % 2 == 0) && (a_kmajor ? (k % 2 == 0) : (m % 2 == 0)) &&
                          ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C) |
                            reinterpret_cast<uintptr_t>(workspace)) % 16 == 0);
-    if (pipe_ok) {
+    const bool small_ok = !in_place && h->dgemm_dmma >= 2 && scale_k == nullptr && split_k == 1 &&
+                          (int64_t)cdiv(m, BM) * cdiv(n, DBN) * 4 < h->sm_count;
+    if (small_ok) {
+        dim3 grid(cdiv(n, SBN), cdiv(m, SBM), 1);
+#define RVGP_GEMM(AK, BKM) dgemm_small_kernel<AK, BKM><<<grid, 128, 0, h->stream>>>(m, n, k, alpha, A, lda, B, ldb, C, ldc, beta, lower_only)
+        if (a_kmajor && b_kmajor) RVGP_GEMM(true, true);
+        else if (a_kmajor && !b_kmajor) RVGP_GEMM(true, false);
+        else if (!a_kmajor && b_kmajor) RVGP_GEMM(false, true);
+        else RVGP_GEMM(false, false);
+#undef RVGP_GEMM
+    } else if (pipe_ok) {
         if (!h->dgemm_pipe_attr) {
             RVGP_CUDA_OK(h, cudaFuncSetAttribute(dgemm_dmma_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_SMEM));
             RVGP_CUDA_OK(h, cudaFuncSetAttribute(dgemm_dmma_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_SMEM));

@@ -169,6 +169,39 @@ def test_small_k_fused_kernel_matches_oracle(k):
         np.testing.assert_allclose(v.cpu().numpy(), rv[:, :1], rtol=1e-6, atol=1e-9)
 
 
+@pytest.mark.parametrize("k", [65, 100, 129, 200, 500])
+def test_rank_k_evaluation_kernels_match_oracle(k):
+    """K15b (64 < k): build + blocked Cholesky + the fused forward-solve / back-solve kernels, captured and replayed as a CUDA
+    graph, against the dense GPflow-style restatement.  k not a multiple of the 64-row panel, repeated evaluations with
+    changing parameters (graph replay), a rank-deficient Gram part (M < k for k = 500) and the not-SPD flag."""
+    from rvgp_b200.gp import DeviceGPR
+    from rvgp_b200._cabi import RvgpError
+    g = load_golden("sphere_n2000_k50")
+    rng = np.random.default_rng(k)
+    M = 420
+    Phi = np.concatenate([g["evecs_Lc"][rng.choice(6000, M, replace=False)][:, :50], rng.normal(size=(M, k - 50)) / np.sqrt(6000)], 1)
+    lam = np.sort(np.concatenate([g["evals_Lc"][:50], 0.7 + 3 * rng.uniform(size=k - 50)]))
+    Y = rng.normal(size=(M, 1))
+    gp = DeviceGPR(_t(Phi), _t(Y), solver="lowrank")
+    assert not getattr(gp, "_small", False)
+    for rep, (nu, kappa, sf, noise) in enumerate([(1.5, 5.0, 1.0, 1.0), (2.0, 2.0, 0.5, 0.01), (1.5, 5.0, 1.0, 1.0), (2.5, 9.0, 2.0, 0.3)]):
+        S = GO.eval_S(lam, nu, kappa, sf, 6000)
+        lml, dS, dn = gp.lml_and_grads(S, noise)
+        rl, rdS, rdn = GO.gpr_lml_dense(Phi, Y, S, noise, grads=True)
+        assert abs(lml - rl) <= 1e-9 * abs(rl), (rep, lml, rl)
+        np.testing.assert_allclose(dS, rdS, rtol=1e-6, atol=1e-8 * np.abs(rdS).max())
+        assert abs(dn - rdn) <= 1e-6 * abs(rdn)
+    Xn = rng.normal(size=(37, k)) / np.sqrt(6000)
+    m, v = gp.predict(S, noise, _t(Xn))
+    rm, rv = GO.gpr_predict_dense(Phi, Y, S, noise, Xn)
+    np.testing.assert_allclose(m.cpu().numpy(), rm, rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(v.cpu().numpy(), rv[:, :1], rtol=1e-6, atol=1e-9)
+    Sbad = S.copy(); Sbad[k // 2] = -1e12                       # B loses positive definiteness -> flag -> RvgpError
+    with pytest.raises((RvgpError, FloatingPointError, ValueError)):
+        with np.errstate(all="raise"):
+            gp.lml_and_grads(Sbad, noise)
+
+
 def test_eeg_shaped_many_fits_on_fixed_eigenbasis():
     """Config C3 shape: one data object, one GP fit per frame on a fixed eigenbasis (eeg_utils.py:26-35)."""
     import time

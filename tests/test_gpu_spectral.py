@@ -108,6 +108,47 @@ def test_dgemm_layouts(shape, dmma):
     h.set_option("dgemm_dmma", 2)                                   # the handle is shared: back to the default
 
 
+@pytest.mark.parametrize("shape", [(1, 1, 1), (37, 53, 100), (200, 129, 257), (436, 192, 64), (244, 244, 256)])
+def test_dgemm_small_tile_kernel(shape):
+    """The 32 x 32-tile DMMA kernel that small products (the Cholesky panels of the rank-k GP evaluation) are routed to: all four
+    operand layouts, ragged edges, accumulate, lower-triangle-only; against numpy and the 128 x 64-tile kernel."""
+    from rvgp_b200._cabi import get_handle, I64
+    m, n, k = shape
+    h = get_handle(0)
+    rng = np.random.default_rng(2)
+    A = rng.normal(size=(m, k)); B = rng.normal(size=(k, n)); C0 = rng.normal(size=(m, n))
+    ref = C0 - A @ B
+    tol = 1e-13 * k ** 0.5 * max(1, np.abs(ref).max())
+    try:
+        for akm in (0, 1):
+            for bkm in (0, 1):
+                Ad = torch.from_numpy(np.ascontiguousarray(A if akm else A.T)).to(_dev())
+                Bd = torch.from_numpy(np.ascontiguousarray(B.T if bkm else B)).to(_dev())
+                outs = []
+                for mode in (2, 1):
+                    h.set_option("dgemm_dmma", mode)
+                    C = torch.zeros((m, n + 1), dtype=torch.float64, device=_dev())
+                    C[:, :n] = torch.from_numpy(C0).to(_dev())
+                    h.call("rvgp_dgemm_acc_f64", int(m), int(n), I64(k), -1.0, Ad, I64(Ad.stride(0)), int(akm), Bd, I64(Bd.stride(0)),
+                           int(bkm), 1.0, C, I64(n + 1))
+                    assert C[:, n].abs().max().item() == 0.0
+                    outs.append(C[:, :n].cpu().numpy())
+                    assert np.abs(outs[-1] - ref).max() <= tol, (akm, bkm, mode)
+                assert np.abs(outs[0] - outs[1]).max() <= tol
+        if m == n:
+            h.set_option("dgemm_dmma", 2)
+            Ad = torch.from_numpy(A).to(_dev())
+            G = torch.full((m, m), 7.0, dtype=torch.float64, device=_dev())
+            h.call("rvgp_dgemm_lower_f64", int(m), int(m), I64(k), 1.0, Ad, I64(k), 1, Ad, I64(k), 1, G, I64(m), 1, None)
+            Gh = G.cpu().numpy(); full = A @ A.T
+            il = np.tril_indices(m)
+            assert np.abs(Gh[il] - full[il]).max() <= 1e-13 * k ** 0.5 * np.abs(full).max()
+            iu = np.triu_indices(m, 32)                               # tiles strictly above the diagonal are never touched
+            assert (Gh[iu] == 7.0).all()
+    finally:
+        h.set_option("dgemm_dmma", 2)
+
+
 @pytest.mark.parametrize("shape", [(2, 2, 2), (64, 64, 100001), (130, 66, 4098), (704, 64, 50000), (50001 * 2, 64, 192),
                                    (3000, 130, 66), (256, 256, 70000)])
 def test_dgemm_pipelined_kernel(shape):

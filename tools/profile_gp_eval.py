@@ -31,3 +31,23 @@ for i in range(reps):
     gp.lml_and_grads(S * (1 + 1e-3 * i), 0.1)
 t1 = time.perf_counter()
 print("k=%d  wall time per lml_and_grads: %.3f ms" % (k, (t1 - t0) / reps * 1e3))
+# per-kernel device time inside the replayed graph (CUPTI)
+import collections
+from torch.profiler import profile, ProfilerActivity
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    for _ in range(20):
+        h.call("rvgp_gp_lowrank_eval_f64", int(k), gp._Gd, gp._bd, gp._par_d, gp._out_d, gp._ev_ws, I64(gp._ev_wsb))
+    torch.cuda.synchronize()
+agg = collections.defaultdict(lambda: [0, 0.0])
+t_first, t_last = None, None
+for ev in prof.events():
+    if ev.device_type == torch.autograd.DeviceType.CUDA:
+        name = ev.name.split("<")[0].split("(")[0].replace("void ", "").replace("rvgp::", "")
+        agg[name][0] += 1
+        agg[name][1] += ev.device_time
+        s0 = ev.time_range.start
+        t_first = s0 if t_first is None else min(t_first, s0)
+        t_last = max(t_last or 0, ev.time_range.end)
+print("span per evaluation %.1f us; busy %.1f us" % ((t_last - t_first) / 20, sum(a[1] for a in agg.values()) / 20))
+for name, (cnt, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+    print("  %-40s per eval: launches %5.1f  us %8.1f  avg us %7.1f" % (name[:40], cnt / 20, us / 20, us / cnt))

@@ -129,6 +129,7 @@ def one_step(X, V, train_ind, test_ind, k, device_out):
     d.timings.update({"create_data_object_total": t1 - t0, "fit": t2 - t1, "transform": t3 - t2})
     summ = {"stats": d.stats, "timings": dict(d.timings), "sharded": bool(getattr(d, "sharded", False)),
             "d": int(A.d), "Lc_rows": int(A.nrows), "Lc_matrix_bytes": int(A.spmm_bytes(0)),
+            "mma_plan": d.stats.get("mma_plan"),
             "gp": {"solver": getattr(gp, "solver", None), "l2_error": getattr(gp, "l2_error", None),
                    "evaluations": getattr(getattr(gp, "_gpr", None), "n_eval", None),
                    "row_sharded": getattr(gp, "comm", None) is not None}}
@@ -242,6 +243,14 @@ def run_b200(args):
                 "bytes_per_launch_survey_formula": int(st["spmm_bytes_plain"]),
                 "frac_survey_formula": round(st["spmm_bytes_plain"] / t_launch / 1e9 / peak, 4),
                 "share_of_step": round(float(share), 3)}
+    mp = s_last.get("mma_plan")
+    if mp and str(st.get("spmm_kernel")).startswith("mma_native"):
+        # executed (zero-padded) tensor work of one launch: every k-step issues 2 DMMA m8n8k4 (512 flop each) per 16 columns
+        dmma_flop = mp["ksteps"] * (panel // 16) * 2 * 512.0
+        roofline["fp64_tensor"] = {"ksteps_per_launch": mp["ksteps"], "fragment_fill": round(mp["fill"], 3),
+                                   "executed_tflops": round(dmma_flop / t_launch / 1e12, 2), "peak_tflops": 37.0,
+                                   "peak_source": "profiles/r01_fp64_peak_b200.txt (DMMA, measured)",
+                                   "note": "co-limit: the padded fragments keep the FP64 tensor pipe this busy while the kernel streams at `frac` of HBM peak (DESIGN.md K9)"}
     if stL.get("filter_launches"):
         tL = float(np.mean([s["stats"]["eig_L"]["t_filter"] / max(1, s["stats"]["eig_L"]["filter_launches"]) for s in summs]))
         roofline["scalar_L"] = {"kernel": str(stL.get("spmm_kernel")), "columns": stL["panel"], "avg_launch_ms": round(tL * 1e3, 4),

@@ -41,7 +41,10 @@ int rvgp_sm_count(rvgp_handle_t h);
 /* kernels launched through this handle since creation (bench.py "gpu_launches") */
 unsigned long long rvgp_launch_count(rvgp_handle_t h);
 int rvgp_version(void);
-/* tuning knobs for experiments: "spmm_lpr" = lanes per block row in rvgp_bsr_spmm_f64 (0 auto | 8 | 16 | 32) */
+/* tuning knobs for experiments: "spmm_lpr" = lanes per block row in rvgp_bsr_spmm_f64 (0 auto | 8 | 16 | 32);
+ * "dgemm_dmma" = FP64 GEMM kernel family (0 DFMA register tile | 1 DMMA, register-staged | 2 (default) DMMA with the
+ * cp.async-pipelined 128x64 tile for large products and the 32x32 tile for small ones); "mma_variant", "mma_variant_n2",
+ * "mma_prefetch", "mma_stream_policy", "mma_gpw" = schedule of the MMA SpMM; "gp_graph" = CUDA-graph replay of K15b. */
 int rvgp_set_option(rvgp_handle_t h, const char* key, int value);
 
 /* ---- K9: block-CSR SpMM (replaces the ARPACK mat-vec inside geometry.py:73) ------------------------
@@ -309,8 +312,10 @@ int rvgp_add_diag_f64(rvgp_handle_t h, double* A, int64_t lda, int n, double v);
 int rvgp_logdiag_sum_f64(rvgp_handle_t h, const double* A, int64_t lda, int n, double* out);
 int rvgp_kdiag_f64(rvgp_handle_t h, const double* X, int64_t ldx, int64_t n, int k, const double* S, double* out);
 
-/* ---- K15b: one rank-k GP evaluation for k > 64 enqueued as a whole (build B = I + S^1/2 G S^1/2 / noise, Cholesky, three
- * triangular solves, column norms, log-determinant): the L-BFGS-B loop of train_gp (main.py:87-95) then costs one small
+/* ---- K15b: one rank-k GP evaluation for k > 64 enqueued as a whole (build B = I + S^1/2 G S^1/2 / noise, blocked Cholesky,
+ * ONE forward-substitution kernel over 8-column slices of [S^1/2 G | S^1/2 b] that also reduces the column norms, ONE
+ * back-substitution / log-determinant / packing kernel; the panel-by-panel rvgp_trsm_f64 route remains for k > 3200), captured
+ * once per fit and replayed as a CUDA graph: the L-BFGS-B loop of train_gp (main.py:87-95) then costs one small
  * host->device copy (par = [S (k), noise]), this call and one device->host copy of out per evaluation.
  * out (2 + 2k doubles): [not-SPD flag, sum log L_ii, z = B^-1 (S^1/2 b), qs_j = ||L^-1 (S^1/2 G) e_j||^2]. */
 int rvgp_gp_lowrank_eval_f64(rvgp_handle_t h, int k, const double* G, const double* b, const double* par, double* out,

@@ -242,6 +242,8 @@ class data:
         eig_Lc = smallest_eigenpairs_paired if self.stats["paired"] else smallest_eigenpairs
         if dim_man == 2 and not shard and n >= 64 and os.environ.get("RVGP_SPMM_MMA", "1") != "0":
             self.stats["spmm_mma"] = A_eig.enable_mma() is not None
+            if self.stats["spmm_mma"]:          # k-step plan of K9 (bench.py: executed FP64-tensor work per launch)
+                self.stats["mma_plan"] = {"ksteps": int(A_eig.mma["ksteps"]), "fill": float(A_eig.mma["fill"])}
         if not shard and os.environ.get("RVGP_SPMM_MMA_L", "1") != "0":
             # K9 for the scalar Laplacian: the same FP64-MMA kernel as L (x) I_2, no matrix values streamed (spmm_mma.cu AMODE 2)
             self.stats["spmm_mma_L"] = A_L.enable_mma_pattern() is not None

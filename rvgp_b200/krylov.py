@@ -231,11 +231,16 @@ def _rho_inverse(theta, cut, hi, lo, d):
 def krylov_eigenpairs(*args, **kwargs):
     """Smallest k eigenpairs by filtered block Lanczos (see _krylov_eigenpairs for the arguments).  ONE BLAS thread limit is held
     for the whole run: the b x b host factorisations of the block loop are far cheaper than entering / leaving the limit."""
+    # experiment knobs (tools / sweeps only): filter strength per block in nats, block width
+    if "RVGP_KRYLOV_NATS" in _os.environ:
+        kwargs.setdefault("nats", float(_os.environ["RVGP_KRYLOV_NATS"]))
+    if "RVGP_KRYLOV_BLOCK" in _os.environ:
+        kwargs.setdefault("block", int(_os.environ["RVGP_KRYLOV_BLOCK"]))
     with _lapack_ctx():
         return _krylov_eigenpairs(*args, **kwargs)
 
 
-def _krylov_eigenpairs(A, k, upper_bound, cut, lam_k, paired=False, tol=1e-12, block=64, nats=4.0, seed=0, stats=None, comm=None,
+def _krylov_eigenpairs(A, k, upper_bound, cut, lam_k, paired=False, tol=1e-12, block=64, nats=3.5, seed=0, stats=None, comm=None,
                       refine_bound=True, lower_bound=0.0, cap_cols=None, max_blocks=400, init_fn=None, verbose=False,
                       _depth=0, _hi=None):
     """Smallest k eigenpairs of the symmetric PSD operator ``A`` (BsrMatrix / ShardedBsr) by filtered block Lanczos.

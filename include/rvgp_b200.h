@@ -365,13 +365,18 @@ int rvgp_vectorfield_features_f64(rvgp_handle_t h, int n, int k, const double* p
  *   unlabelled, +-1 = node sign; seed at least one node before the first call; *changed is set when any label was written.
  * rvgp_orient_check: out2[0] = number of stored off-diagonal blocks with s_i s_j det(block) < 0, out2[1] = unlabelled nodes.
  * rvgp_rot90_nodes_f64: out = J V, (J V)[2i] = -V[2i+1], (J V)[2i+1] = V[2i] (out must not alias V).
- * rvgp_flip_odd_rows_f64: V[2i+1, :] *= s[i] (apply D to a block vector, or to the second gauge coordinate). */
+ * rvgp_flip_odd_rows_f64: V[2i+1, :] *= s[i] (apply D to a block vector, or to the second gauge coordinate).
+ * rvgp_pair_panel_f64: out (2n x 2b) = [V | J V]; rvgp_pair_combine_f64: W = beta W + alpha (T[:, :b] + J T[:, b:2b]) -- the two
+ *   halves of the complex block algebra of the paired eigensolver, so that C^H W and V C are ONE real GEMM each (krylov.py). */
 int rvgp_orient_steps(rvgp_handle_t h, int n, const int32_t* indptr, const int32_t* indices, const double* vals,
                       int32_t* labels, int32_t* changed, int steps);
 int rvgp_orient_check(rvgp_handle_t h, int n, const int32_t* indptr, const int32_t* indices, const double* vals,
                       const int32_t* labels, int32_t* out2);
 int rvgp_rot90_nodes_f64(rvgp_handle_t h, int64_t nnodes, int ncols, const double* V, int64_t ldv, double* out, int64_t ldo);
 int rvgp_flip_odd_rows_f64(rvgp_handle_t h, int64_t nnodes, int ncols, const int32_t* s, double* V, int64_t ldv);
+int rvgp_pair_panel_f64(rvgp_handle_t h, int64_t nnodes, int ncols, const double* V, int64_t ldv, double* out, int64_t ldo);
+int rvgp_pair_combine_f64(rvgp_handle_t h, int64_t nnodes, int ncols, const double* T, int64_t ldt, double alpha, double beta,
+                          double* W, int64_t ldw);
 
 #ifdef __cplusplus
 }

@@ -67,6 +67,37 @@ __global__ void rot90_nodes_kernel(int64_t nnodes, int ncols, const double* __re
     out[(2 * i + 1) * ldo + c] = x;
 }
 
+// Paired (complex-Hermitian) block algebra on real storage: a complex block W is one real (2 n x b) panel, i W = J W.
+// pair_panel:   out (2 n x 2 b) = [V | J V]: ONE tall-skinny Gram  C^T [W | J W]  then yields Re and -Im of  C^H W  together.
+// pair_combine: W = beta W + alpha (T[:, :b] + J T[:, b:2b]): ONE product  T = V [Re C | Im C]  then gives  V C = V Re C + J (V Im C).
+__global__ void pair_panel_kernel(int64_t nnodes, int ncols, const double* __restrict__ V, int64_t ldv, double* __restrict__ out,
+                                  int64_t ldo) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nnodes * ncols) return;
+    const int64_t i = idx / ncols;
+    const int c = (int)(idx % ncols);
+    const double x = V[(2 * i) * ldv + c], y = V[(2 * i + 1) * ldv + c];
+    out[(2 * i) * ldo + c] = x;
+    out[(2 * i + 1) * ldo + c] = y;
+    out[(2 * i) * ldo + ncols + c] = -y;
+    out[(2 * i + 1) * ldo + ncols + c] = x;
+}
+
+__global__ void pair_combine_kernel(int64_t nnodes, int ncols, const double* __restrict__ T, int64_t ldt, double alpha, double beta,
+                                    double* __restrict__ W, int64_t ldw) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nnodes * ncols) return;
+    const int64_t i = idx / ncols;
+    const int c = (int)(idx % ncols);
+    const double rx = T[(2 * i) * ldt + c], ry = T[(2 * i + 1) * ldt + c];
+    const double ix = T[(2 * i) * ldt + ncols + c], iy = T[(2 * i + 1) * ldt + ncols + c];
+    double* w0 = W + (2 * i) * ldw + c;
+    double* w1 = W + (2 * i + 1) * ldw + c;
+    const double v0 = alpha * (rx - iy), v1 = alpha * (ry + ix);        // (J t)[2i] = -t[2i+1], (J t)[2i+1] = t[2i]
+    *w0 = (beta != 0.0) ? fma(beta, *w0, v0) : v0;
+    *w1 = (beta != 0.0) ? fma(beta, *w1, v1) : v1;
+}
+
 // V[2i+1, :] *= s[i]   (the similarity transform D = diag(1, s_i) applied to block vectors / gauges' second coordinate)
 __global__ void flip_odd_rows_kernel(int64_t nnodes, int ncols, const int* __restrict__ s, double* __restrict__ V, int64_t ldv) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -108,6 +139,26 @@ extern "C" int rvgp_rot90_nodes_f64(rvgp_handle_t hh, int64_t nnodes, int ncols,
     if (nnodes * ncols == 0) return RVGP_OK;
     rot90_nodes_kernel<<<cdiv(nnodes * ncols, 256), 256, 0, h->stream>>>(nnodes, ncols, V, ldv, out, ldo);
     RVGP_LAUNCH_OK(h, "rot90_nodes_kernel");
+    return RVGP_OK;
+}
+
+extern "C" int rvgp_pair_panel_f64(rvgp_handle_t hh, int64_t nnodes, int ncols, const double* V, int64_t ldv, double* out,
+                                   int64_t ldo) {
+    Handle* h = H(hh);
+    RVGP_REQUIRE(h, nnodes >= 0 && ncols >= 0 && V != out && ldo >= 2 * (int64_t)ncols, "pair_panel: bad arguments");
+    if (nnodes * ncols == 0) return RVGP_OK;
+    pair_panel_kernel<<<cdiv(nnodes * ncols, 256), 256, 0, h->stream>>>(nnodes, ncols, V, ldv, out, ldo);
+    RVGP_LAUNCH_OK(h, "pair_panel_kernel");
+    return RVGP_OK;
+}
+
+extern "C" int rvgp_pair_combine_f64(rvgp_handle_t hh, int64_t nnodes, int ncols, const double* T, int64_t ldt, double alpha,
+                                     double beta, double* W, int64_t ldw) {
+    Handle* h = H(hh);
+    RVGP_REQUIRE(h, nnodes >= 0 && ncols >= 0 && T != W && ldt >= 2 * (int64_t)ncols, "pair_combine: bad arguments");
+    if (nnodes * ncols == 0) return RVGP_OK;
+    pair_combine_kernel<<<cdiv(nnodes * ncols, 256), 256, 0, h->stream>>>(nnodes, ncols, T, ldt, alpha, beta, W, ldw);
+    RVGP_LAUNCH_OK(h, "pair_combine_kernel");
     return RVGP_OK;
 }
 

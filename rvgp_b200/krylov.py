@@ -50,6 +50,10 @@ class FieldOps:
         # (the N rows) is split until ~3 CTAs per SM are in flight: split * tiles <= 3 * SMs
         self.ws = torch.empty(3 * h.sm_count * 128 * 64 + cap * b, dtype=torch.float64, device=dev)
         self.tmp = torch.empty((N, b), dtype=torch.float64, device=dev)           # J W / V Im(C) scratch
+        # paired mode: [W | J W] and V [Re C | Im C] panels (N x 2b) and their (cap x 2b) coefficients, so that C^H W and V C are
+        # ONE real GEMM each (V, the large operand, is read once instead of twice; a b = 32 block fills the 64-column GEMM tile)
+        self.pp = torch.empty((N, 2 * b), dtype=torch.float64, device=dev) if cplx else None
+        self.C2 = torch.empty((cap, 2 * b), dtype=torch.float64, device=dev) if cplx else None
         self.flops = 0.0
 
     # ---- primitives --------------------------------------------------------------------------------------------
@@ -75,23 +79,35 @@ class FieldOps:
         self.flops += 2.0 * self.N * cur * nb
 
     # ---- block operations -----------------------------------------------------------------------------------------
+    def _pair(self, W):
+        """(N x 2 nb) panel [W | J W]."""
+        nb = W.shape[1]
+        P = self.pp[:, :2 * nb]
+        self.h.call("rvgp_pair_panel_f64", I64(self.N // 2), int(nb), W, I64(W.stride(0)), P, I64(self.pp.stride(0)))
+        return P
+
+    def _apply_pair(self, Vc, K2, W, alpha, beta):
+        """W = beta W + alpha Vc C for the complex (cur x nb) matrix C given as the device matrix K2 = [Re C | Im C]."""
+        cur, nb = Vc.shape[1], W.shape[1]
+        T = self.pp[:, :2 * nb]
+        self.h.call("rvgp_dgemm_f64", int(self.N), int(2 * nb), I64(cur), 1.0, Vc, I64(Vc.stride(0)), 1, K2, I64(K2.stride(0)), 0, None,
+                    T, I64(self.pp.stride(0)), 1, None)
+        self.flops += 4.0 * self.N * cur * nb
+        self.h.call("rvgp_pair_combine_f64", I64(self.N // 2), int(nb), T, I64(self.pp.stride(0)), float(alpha), float(beta),
+                    W, I64(W.stride(0)))
+
     def project_out(self, Vc, W):
         """One classical Gram-Schmidt pass: C = Vc^H W (all-reduced over the ranks), W -= Vc C.  Returns C on the host."""
         cur, nb = Vc.shape[1], W.shape[1]
-        Cr = self._gram_real(Vc, W, self.Cd)
         if self.cplx:
-            JW = self._rot(W, self.tmp[:, :nb])
-            Ci = self._gram_real(Vc, JW, self.Ci)
+            C2 = self._gram_real(Vc, self._pair(W), self.C2)          # [Vc^T W | Vc^T (J W)] = [Re C | -Im C]
             if self.comm is not None:
-                self.comm.allreduce_(Cr); self.comm.allreduce_(Ci)
-            Ci.neg_()                                        # Im C = -Vc^T (J W)
-            self._acc(Vc, Cr, W, -1.0)                       # W -= Vc Re C
-            t = self.tmp[:, :nb]
-            self.h.call("rvgp_dgemm_f64", int(self.N), int(nb), I64(cur), 1.0, Vc, I64(Vc.stride(0)), 1, Ci, I64(self.Ci.stride(0)),
-                        0, None, t, I64(t.stride(0)), 1, None)
-            self.flops += 2.0 * self.N * cur * nb
-            self._sub_rot(W, t)                              # W -= J (Vc Im C)
-            return Cr.cpu().numpy() + 1j * Ci.cpu().numpy()
+                self.comm.allreduce_(C2)
+            C2[:, nb:].neg_()
+            self._apply_pair(Vc, C2, W, -1.0, 1.0)                    # W -= Vc Re C + J (Vc Im C)
+            Ch = C2.cpu().numpy()
+            return Ch[:, :nb] + 1j * Ch[:, nb:]
+        Cr = self._gram_real(Vc, W, self.Cd)
         if self.comm is not None:
             self.comm.allreduce_(Cr)
         self._acc(Vc, Cr, W, -1.0)
@@ -108,14 +124,14 @@ class FieldOps:
     def gram_self(self, W):
         """W^H W on the host (Hermitian / symmetric)."""
         nb = W.shape[1]
-        Gr = self._gram_real(W, W, self.Cd)
         if self.cplx:
-            JW = self._rot(W, self.tmp[:, :nb])
-            Gi = self._gram_real(W, JW, self.Ci)
+            G2 = self._gram_real(W, self._pair(W), self.C2)           # [W^T W | W^T (J W)]
             if self.comm is not None:
-                self.comm.allreduce_(Gr); self.comm.allreduce_(Gi)
-            G = Gr.cpu().numpy() - 1j * Gi.cpu().numpy()
+                self.comm.allreduce_(G2)
+            Gh = G2.cpu().numpy()
+            G = Gh[:, :nb] - 1j * Gh[:, nb:]
             return 0.5 * (G + G.conj().T)
+        Gr = self._gram_real(W, W, self.Cd)
         if self.comm is not None:
             self.comm.allreduce_(Gr)
         G = Gr.cpu().numpy()
@@ -130,17 +146,21 @@ class FieldOps:
         else:
             Md = torch.from_numpy(np.ascontiguousarray(M.real if self.cplx else M, dtype=np.float64)).to(self.dev)
             Mi = torch.from_numpy(np.ascontiguousarray(M.imag, dtype=np.float64)).to(self.dev) if self.cplx else None
+        if Mi is not None:
+            # complex M: per panel of b columns one product with [Re M | Im M] and one combine (out = T_re + J T_im)
+            if not hasattr(self, "_K2"):
+                self._K2 = torch.empty((self.cap, 2 * self.b), dtype=torch.float64, device=self.dev)
+            for c0 in range(0, p, self.b):
+                c1 = min(p, c0 + self.b)
+                w = c1 - c0
+                K2 = self._K2[:cur, :2 * w]
+                K2[:, :w].copy_(Md[:, c0:c1])
+                K2[:, w:].copy_(Mi[:, c0:c1])
+                self._apply_pair(Vc, K2, out[:, c0:c1], 1.0, 0.0)
+            return out
         self.h.call("rvgp_dgemm_f64", int(self.N), int(p), I64(cur), 1.0, Vc, I64(Vc.stride(0)), 1, Md, I64(Md.stride(0)), 0, None,
                     out, I64(out.stride(0)), 1, None)
         self.flops += 2.0 * self.N * cur * p
-        if Mi is not None:
-            for c0 in range(0, p, self.b):                   # out += J (Vc Im M), one scratch panel at a time
-                c1 = min(p, c0 + self.b)
-                t = self.tmp[:, :c1 - c0]
-                self.h.call("rvgp_dgemm_f64", int(self.N), int(c1 - c0), I64(cur), -1.0, Vc, I64(Vc.stride(0)), 1, Mi[:, c0:c1],
-                            I64(Mi.stride(0)), 0, None, t, I64(t.stride(0)), 1, None)
-                self._sub_rot(out[:, c0:c1], t)              # out -= J (-(Vc Im M)) = out + J (Vc Im M)
-                self.flops += 2.0 * self.N * cur * (c1 - c0)
         return out
 
     def cholqr2(self, W, out, st):
@@ -236,6 +256,12 @@ def krylov_eigenpairs(*args, **kwargs):
         kwargs.setdefault("nats", float(_os.environ["RVGP_KRYLOV_NATS"]))
     if "RVGP_KRYLOV_BLOCK" in _os.environ:
         kwargs.setdefault("block", int(_os.environ["RVGP_KRYLOV_BLOCK"]))
+    if kwargs.get("paired"):
+        # complex blocks of 32: [W | J W] is then exactly one 64-column GEMM / SpMM panel, and the narrower block buys a higher Krylov
+        # power per column (B200, C4: eig_Lc 2.45 -> 2.19 s already with the unbatched algebra; 96-column blocks: 4.2 s)
+        if "RVGP_KRYLOV_NATS_PAIRED" in _os.environ:
+            kwargs["nats"] = float(_os.environ["RVGP_KRYLOV_NATS_PAIRED"])
+        kwargs.setdefault("block", int(_os.environ.get("RVGP_KRYLOV_BLOCK_PAIRED", "32")))
     with _lapack_ctx():
         return _krylov_eigenpairs(*args, **kwargs)
 
@@ -278,7 +304,9 @@ def _krylov_eigenpairs(A, k, upper_bound, cut, lam_k, paired=False, tol=1e-12, b
     f = math.acosh(2.0 * math.cosh(d * gk) - 1.0)
     nblk_est = math.ceil(kw / b) + math.ceil(40.0 / f) + 2
     keep = kw + 2 * b                                    # Ritz vectors kept at a thick restart
-    cap = (nblk_est + 3) * b if cap_cols is None else int(cap_cols)
+    # spare blocks: the estimate is tight for 64-column blocks and ~15 % short for 32-column ones (the convergence phase of a
+    # narrower block is longer); a thick restart costs more than the memory
+    cap = (nblk_est + max(3, math.ceil(0.3 * nblk_est))) * b if cap_cols is None else int(cap_cols)
     cap = max(cap, keep + 4 * b)
     cap = min(cap, (nfield // b) * b)
     st = stats if stats is not None else {}

@@ -228,6 +228,30 @@ def _fake_dgemm_lower(self, m, n, k, alpha, A, lda, a_kmajor, B, ldb, b_kmajor, 
 
 FakeHandle.rvgp_fill_uniform_f64 = _fake_fill_uniform
 FakeHandle.rvgp_rot90_nodes_f64 = _fake_rot90
+
+
+def _fake_pair_panel(self, nnodes, ncols, V, ldv, out, ldo):
+    Vm, Om = _mat(V, 2 * nnodes, ncols, ldv), _mat(out, 2 * nnodes, 2 * ncols, ldo)
+    Om[:, :ncols] = Vm
+    Om[0::2, ncols:] = -Vm[1::2]
+    Om[1::2, ncols:] = Vm[0::2]
+    return 0
+
+
+def _fake_pair_combine(self, nnodes, ncols, T, ldt, alpha, beta, W, ldw):
+    Tm, Wm = _mat(T, 2 * nnodes, 2 * ncols, ldt), _mat(W, 2 * nnodes, ncols, ldw)
+    v = Tm[:, :ncols].clone()
+    v[0::2] -= Tm[1::2, ncols:]
+    v[1::2] += Tm[0::2, ncols:]
+    if beta != 0.0:
+        Wm.mul_(beta).add_(alpha * v)
+    else:
+        Wm.copy_(alpha * v)
+    return 0
+
+
+FakeHandle.rvgp_pair_panel_f64 = _fake_pair_panel
+FakeHandle.rvgp_pair_combine_f64 = _fake_pair_combine
 FakeHandle.rvgp_resid_sq_f64 = _fake_resid_sq
 FakeHandle.rvgp_dgemm_lower_f64 = _fake_dgemm_lower
 

@@ -230,7 +230,9 @@ def run_b200(args):
         try:
             traffic = json.load(open(tp)).get(wl)
             if isinstance(traffic, dict):
-                traffic = traffic.get(str(st.get("spmm_kernel", "gather")).split(" ")[0])
+                # one ncu capture per (kernel, panel width): "<kernel>_b<columns>", the bare key being the 64-column capture
+                key = str(st.get("spmm_kernel", "gather")).split(" ")[0]
+                traffic = traffic.get("%s_b%d" % (key, st["panel"]), traffic.get(key) if st["panel"] == 64 else None)
         except Exception:
             traffic = None
     kname = ("bsr_spmm_mma_native_kernel (FP64 mma.sync row-group SpMM, node-contiguous panels; fused Chebyshev step, d=%d, %d columns)"

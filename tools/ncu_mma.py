@@ -1,5 +1,5 @@
 """Run a few fused launches of the shipped FP64-MMA SpMM (node-contiguous panels) for ncu.
-usage: ncu_mma.py torus 1000000 [variant]"""
+usage: [RVGP_NCU_B=32] ncu_mma.py torus 1000000 [variant]   (RVGP_NCU_B: complex columns of the Lc panel, default 64)"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -10,7 +10,7 @@ A, L, _ = build(kind, n)
 A.enable_mma()
 if len(sys.argv) > 3:
     get_handle(0).set_option("mma_variant", int(sys.argv[3]))
-b = 64
+b = int(os.environ.get("RVGP_NCU_B", "64"))
 bufs = [torch.randn((A.nbrows, 2 * b), dtype=torch.float64, device="cuda") for _ in range(3)]
 for i in range(6):
     A.spmm_native(bufs[(i + 1) % 3], bufs[(i + 2) % 3], alpha=0.03, beta=-0.2, gamma=0.1, Wn=bufs[i % 3])

@@ -72,6 +72,46 @@ def test_rot90_and_flip_kernels():
     assert np.array_equal(Vd.cpu().numpy(), ref2)
 
 
+def test_pair_panel_and_combine_kernels_give_the_complex_products():
+    """The two halves of the batched complex block algebra (krylov.FieldOps): with z = x + i y stored as the real (2n)-vector
+    (x_0, y_0, x_1, y_1, ...) and i z = J z,  V^T [W | J W] = [Re V^H W | -Im V^H W]  and  T_re + J T_im = V C  for
+    T = V [Re C | Im C]; strided inputs, both beta branches of the combine."""
+    from rvgp_b200._cabi import get_handle, I64
+    from rvgp_b200.krylov import FieldOps
+    h = get_handle(0)
+    rng = np.random.default_rng(3)
+    n, b, cur = 41, 6, 10
+    W = rng.normal(size=(2 * n, b + 3)); V = rng.normal(size=(2 * n, cur))
+    Wd, Vd = _t(W), _t(V)
+    P = torch.zeros((2 * n, 2 * b + 1), dtype=torch.float64, device=Wd.device)
+    h.call("rvgp_pair_panel_f64", I64(n), b, Wd, I64(b + 3), P, I64(2 * b + 1))
+    Ph = P.cpu().numpy()
+    JW = np.empty((2 * n, b)); JW[0::2] = -W[1::2, :b]; JW[1::2] = W[0::2, :b]
+    assert np.array_equal(Ph[:, :b], W[:, :b]) and np.array_equal(Ph[:, b:2 * b], JW) and not Ph[:, 2 * b].any()
+    cplx = lambda A: A[0::2] + 1j * A[1::2]
+    Vc, Wc = cplx(V), cplx(W[:, :b])
+    C = Vc.conj().T @ Wc
+    G2 = V.T @ Ph[:, :2 * b]
+    np.testing.assert_allclose(G2[:, :b], C.real, atol=1e-13)
+    np.testing.assert_allclose(G2[:, b:], -C.imag, atol=1e-13)
+    T = _t(V @ np.concatenate([C.real, C.imag], 1))
+    for beta in (0.0, 1.0):
+        out = _t(W[:, :b].copy())
+        h.call("rvgp_pair_combine_f64", I64(n), b, T, I64(2 * b), -1.0, beta, out, I64(b))
+        np.testing.assert_allclose(cplx(out.cpu().numpy()), beta * Wc - Vc @ C, atol=1e-12)
+    # and through the block operations themselves: one Gram-Schmidt pass leaves W orthogonal to V in the complex inner product
+    Q = np.linalg.qr(Vc)[0]
+    Vq = np.empty((2 * n, cur)); Vq[0::2] = Q.real; Vq[1::2] = Q.imag
+    ops = FieldOps(h, 2 * n, 16, 8, Wd.device, None, True)
+    Wb = _t(W[:, :b].copy())
+    Ch = ops.project_out(_t(Vq), Wb)
+    np.testing.assert_allclose(Ch, Q.conj().T @ Wc, atol=1e-12)
+    assert np.abs(Q.conj().T @ cplx(Wb.cpu().numpy())).max() < 1e-12
+    G = ops.gram_self(Wb)
+    Wn = cplx(Wb.cpu().numpy())
+    np.testing.assert_allclose(G, Wn.conj().T @ Wn, atol=1e-12)
+
+
 def test_paired_solver_equals_real_solver_and_golden():
     """Direct call on the golden sphere Lc: re-orient, solve in paired mode, un-flip, compare with ARPACK's golden output."""
     from rvgp_b200 import geometry as geo

@@ -1,5 +1,5 @@
 """Krylov eigensolver on large problems other than the benchmark torus: does the cut estimation hold, does it converge without
-retries / restarts, how long does it take?  usage: python tools/robustness_check.py"""
+retries / restarts, how long does it take?  usage: python tools/robustness_check.py [kind ...]"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -7,7 +7,10 @@ import RVGP
 from tests.workloads import make_cloud
 cases = [("sphere", 1000000, 500, {}), ("manifold5_R32", 200000, 300, dict(n_neighbors=22, explained_variance=0.9)),
          ("torus", 300000, 256, {}), ("moebius", 400000, 200, {})]
+only = set(sys.argv[1:])                    # optional: restrict to these cloud kinds
 for kind, n, k, kw in cases:
+    if only and kind not in only:
+        continue
     X = make_cloud(kind, n, 0)
     for rep in range(2):
         torch.cuda.synchronize(); t0 = time.perf_counter()

@@ -113,7 +113,7 @@ class _Model:
                 vals = list(kgrads.values()) + [gnoise, f]
                 if not np.all(np.isfinite(vals)):
                     raise FloatingPointError("non-finite objective")
-        except (FloatingPointError, RvgpError):
+        except (ArithmeticError, RvgpError):          # FloatingPointError, ZeroDivisionError (kappa == 0 in pure-Python floats), OverflowError
             # a trial point of the line search left the domain (non-finite density / non-SPD Gram): report a huge
             # loss so L-BFGS-B backs off (TensorFlow would raise here and abort the fit)
             return 1e50, np.zeros(len(v))

@@ -101,5 +101,5 @@ def test_properties_c4_size():
     for name in ("eig_L", "eig_Lc"):
         st = d.stats[name]
         assert "Lanczos" in str(st.get("solver")) and st["converged"] and st["residual_max"] <= st["tol_abs"]
-        assert st["final_rr_outer"] == 1 and st["restarts"] == 0
+        assert st["final_rr_outer"] <= 1 and st["restarts"] == 0          # 0: the Krylov Ritz vectors were accepted as they are
     torch.cuda.empty_cache()

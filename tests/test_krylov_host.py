@@ -42,7 +42,7 @@ def test_krylov_real_matches_arpack(monkeypatch, cap_cols):
                                      cap_cols=cap_cols)
     _check(L, evals, evecs, k, ref, 1e-12 * hi)
     assert st["converged"] and st["krylov_converged"]
-    assert st["final_rr_outer"] == 1                     # the hand-over needed no ChFSI polishing sweep
+    assert st["final_rr_outer"] <= 1                     # 0: Ritz vectors accepted as they are; 1: one A-space Rayleigh-Ritz, no polishing sweep
     assert (st["restarts"] > 0) == (cap_cols is not None)
     # the point of the method: far fewer column-degrees than subspace iteration needs (~ m * 27 / g per column)
     from rvgp_b200.eigensolver import smallest_eigenpairs

@@ -117,3 +117,25 @@ def test_node_index_validation():
         _as_node_indices(np.ones(9, dtype=bool), n)
     with pytest.raises(IndexError):
         _as_node_indices(np.array([0.5, 1.0]), n)
+
+
+def test_optimiser_glue_rejects_trial_points_outside_the_domain():
+    """A line-search trial point that leaves the domain of the objective -- non-finite density, not-SPD Gram, or plain
+    arithmetic errors such as kappa == 0 in pure-Python floats -- must come back to L-BFGS-B as a huge loss with a zero
+    gradient (a rejected step), not as an exception that aborts the fit (GPflow / TensorFlow would abort, main.py:87-95)."""
+    from rvgp_b200.main import _Model
+    from rvgp_b200._cabi import RvgpError
+
+    class Bad(_Model):
+        def __init__(self, exc):
+            self.exc = exc
+
+        def _evaluate(self):
+            raise self.exc
+
+    for exc in (ZeroDivisionError("float division by zero"), FloatingPointError("non-finite"), OverflowError("x"),
+                RvgpError(-5, "not SPD")):
+        f, g = Bad(exc)._loss_and_grad(np.zeros(3), [])
+        assert f == 1e50 and g.shape == (3,) and not g.any()
+    with pytest.raises(KeyError):                       # anything else is a bug and must surface
+        Bad(KeyError("x"))._loss_and_grad(np.zeros(3), [])

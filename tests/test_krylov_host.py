@@ -29,10 +29,11 @@ def _check(A, evals, evecs, k, ref, tol_abs):
     assert np.abs(U.T @ U - np.eye(k)).max() < 1e-9
 
 
-@pytest.mark.parametrize("cap_cols", [None, 224])          # None: no restart needed; 224: forces thick restarts
-def test_krylov_real_matches_arpack(monkeypatch, cap_cols):
+@pytest.mark.parametrize("cap_cols,fast_accept", [(None, "1"), (None, "0"), (224, "1")])   # 224 columns: forces thick restarts
+def test_krylov_real_matches_arpack(monkeypatch, cap_cols, fast_accept):
     from rvgp_b200.krylov import krylov_eigenpairs
     fake_cabi.install_eigensolver(monkeypatch)
+    monkeypatch.setenv("RVGP_KRYLOV_FAST_ACCEPT", fast_accept)
     L, hi = _laplacian(3000)
     k = 40
     ref = np.sort(spla.eigsh(L, k=90, which="SM", return_eigenvectors=False))
@@ -42,7 +43,7 @@ def test_krylov_real_matches_arpack(monkeypatch, cap_cols):
                                      cap_cols=cap_cols)
     _check(L, evals, evecs, k, ref, 1e-12 * hi)
     assert st["converged"] and st["krylov_converged"]
-    assert st["final_rr_outer"] <= 1                     # 0: Ritz vectors accepted as they are; 1: one A-space Rayleigh-Ritz, no polishing sweep
+    assert st["final_rr_outer"] == (0 if fast_accept == "1" else 1)   # 0: Ritz block accepted as it is; 1: one A-space Rayleigh-Ritz, no polishing
     assert (st["restarts"] > 0) == (cap_cols is not None)
     # the point of the method: far fewer column-degrees than subspace iteration needs (~ m * 27 / g per column)
     from rvgp_b200.eigensolver import smallest_eigenpairs
@@ -64,11 +65,13 @@ def test_krylov_recovers_from_a_cut_below_lambda_k(monkeypatch):
     assert st.get("cut_retries", 0) >= 1 or st["final_rr_outer"] > 1       # it noticed (retry) or ChFSI finished the job
 
 
-def test_krylov_paired_matches_arpack(monkeypatch):
+@pytest.mark.parametrize("fast_accept", ["1", "0"])      # Ritz block accepted directly / ChFSI Rayleigh-Ritz hand-over
+def test_krylov_paired_matches_arpack(monkeypatch, fast_accept):
     """Complex-Hermitian operator in real 2x2-block storage (every block a scaled rotation): eigenvalues come in exact pairs
     and the solver works on half the columns (eigensolver.py paired mode)."""
     from rvgp_b200.krylov import krylov_eigenpairs
     fake_cabi.install_eigensolver(monkeypatch)
+    monkeypatch.setenv("RVGP_KRYLOV_FAST_ACCEPT", fast_accept)
     L, hi = _laplacian(1500, seed=1)
     n = L.shape[0]
     rng = np.random.default_rng(0)
@@ -99,6 +102,7 @@ def test_krylov_paired_matches_arpack(monkeypatch):
                                      paired=True, block=16, stats=st)
     _check(Ar, evals, evecs, k, ref, 1e-12 * hi)
     assert st["converged"] and st["paired"]
+    assert st["final_rr_outer"] == (0 if fast_accept == "1" else 1)
     U = evecs.numpy()
     JU = np.empty_like(U[:, 0::2])
     JU[0::2] = -U[1::2, 0::2]

@@ -321,3 +321,43 @@ def install_eigensolver(monkeypatch):
     monkeypatch.setattr(torch.cuda, "Event", _Ev)
     monkeypatch.setattr(torch.cuda, "synchronize", lambda device=None: None)
     return fh
+
+
+class FakeShardedBsr(FakeBsr):
+    """Row-sharded duck-type of distributed.ShardedBsr for the gloo tests: this rank owns rows [r0, r1) of the global SciPy
+    matrix; every product all-gathers the block vector (the real operator exchanges only the halo rows -- covered by
+    tests/test_distributed_cpu.py::test_sharded_halo_spmm_gloo -- the eigensolvers above it see the same interface)."""
+    spmm_kernel_name = "fake + gloo all-gather"
+
+    def __init__(self, M, r0, r1, counts, comm, d=1):
+        import scipy.sparse as sp
+        super().__init__(sp.csr_matrix(M)[r0:r1], d=d)
+        self.row_offset = int(r0)
+        self.counts, self.comm = list(counts), comm
+
+    def _full(self, X):
+        return self.comm.allgather_rows(X.contiguous(), self.counts).numpy()
+
+    def matmat(self, X, out=None, h=None):
+        Y = torch.from_numpy(self.M @ self._full(X))
+        if out is None:
+            return Y
+        out.copy_(Y)
+        return out
+
+    def cheb_filter(self, Vp, w0, w1, ncols, degree, lo_spec, lo_cut, hi, h=None, w2=None):
+        if degree <= 0:
+            return
+        A = self.M
+        e, c = 0.5 * (hi - lo_cut), 0.5 * (hi + lo_cut)
+        s1 = e / (lo_spec - c)
+        tau, sig = 2.0 / s1, s1
+        X = Vp.clone()
+        Y = torch.from_numpy((A @ self._full(X) - c * X.numpy()) * (s1 / e))
+        for _ in range(2, degree + 1):
+            sn = 1.0 / (tau - sig)
+            Yn = torch.from_numpy((A @ self._full(Y) - c * Y.numpy()) * (2.0 * sn / e) - sig * sn * X.numpy())
+            Y, X = Yn, Y
+            sig = sn
+        Vp.copy_(Y)
+        self.col_degrees += degree * ncols

@@ -150,3 +150,82 @@ def test_sharded_gp_and_geodesic_host_pieces_gloo(world):
     for p in procs:
         p.join(timeout=60)
     assert all(r[1] == "ok" for r in res), res
+
+
+def _worker_krylov(rank, world, port, paired, fast_accept, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["RVGP_KRYLOV_FAST_ACCEPT"] = fast_accept
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import scipy.sparse.linalg as spla
+        from tests import fake_cabi, test_krylov_host as TK
+        from rvgp_b200.distributed import Comm
+        from rvgp_b200.krylov import krylov_eigenpairs
+        mpatch = pytest.MonkeyPatch()
+        fake_cabi.install_eigensolver(mpatch)
+        L, hi = TK._laplacian(1500, seed=1)
+        n = L.shape[0]
+        if paired:
+            # complex-Hermitian "magnetic" Laplacian in real 2x2-block storage (the construction of test_krylov_host.py)
+            rng = np.random.default_rng(0)
+            Lc = sp.coo_matrix(L)
+            phi, data = {}, np.empty(Lc.nnz, dtype=np.complex128)
+            for e, (i, j, v) in enumerate(zip(Lc.row, Lc.col, Lc.data)):
+                if i == j:
+                    data[e] = v
+                else:
+                    key = (min(i, j), max(i, j))
+                    if key not in phi:
+                        phi[key] = rng.uniform(-0.3, 0.3)
+                    data[e] = v * np.exp(1j * (phi[key] if i < j else -phi[key]))
+            Hc = sp.csr_matrix((data, (Lc.row, Lc.col)), shape=(n, n))
+            M = sp.bmat([[Hc.real, -Hc.imag], [Hc.imag, Hc.real]]).tocsr()
+            perm = np.empty(2 * n, dtype=np.int64)
+            perm[0::2] = np.arange(n); perm[1::2] = n + np.arange(n)
+            M = M[perm][:, perm].tocsr()
+            d = 2
+        else:
+            M, d = L, 1
+        k = 30
+        ref = np.sort(spla.eigsh(M, k=70, which="SM", return_eigenvectors=False))
+        nodes = [n * r // world for r in range(world + 1)]          # node boundaries: a complex entry (2 rows) never straddles ranks
+        r0, r1 = nodes[rank] * d, nodes[rank + 1] * d
+        counts = [(nodes[r + 1] - nodes[r]) * d for r in range(world)]
+        comm = Comm()
+        A = fake_cabi.FakeShardedBsr(M, r0, r1, counts, comm, d=d)
+        st = {}
+        evals, evecs = krylov_eigenpairs(A, k, hi, cut=1.05 * ref[int(1.5 * k) + 16], lam_k=ref[k - 1], paired=paired,
+                                         block=16, stats=st, comm=comm)
+        ev = evals.numpy()
+        U = comm.allgather_rows(evecs.contiguous(), counts).numpy()  # global eigenvectors, row blocks in rank order
+        assert np.allclose(ev, ref[:k], rtol=1e-8, atol=1e-10), np.abs(ev - ref[:k]).max()
+        res = np.linalg.norm(M @ U - U * ev, axis=0)
+        assert res.max() <= 1e-12 * hi * 1.0001, res.max()
+        assert np.abs(U.T @ U - np.eye(k)).max() < 1e-9
+        assert st["converged"] and st["world"] == world
+        assert st["final_rr_outer"] == (0 if fast_accept == "1" else 1), st["final_rr_outer"]
+        mpatch.undo()
+        q.put((rank, "ok"))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put((rank, "FAIL: " + traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("paired,fast_accept", [(False, "0"), (True, "0"), (False, "1"), (True, "1")])
+def test_sharded_krylov_eigensolver_gloo(paired, fast_accept):
+    """The filtered block Lanczos solver with its block vectors ROW-SHARDED over 2 ranks (all-reduced Gram matrices, Rayleigh
+    quotients and residuals; real and paired algebra; both hand-over paths) against ARPACK on the global matrix."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_krylov, args=(r, world, port, paired, fast_accept, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] == "ok" for r in res), res
